@@ -1,0 +1,410 @@
+// Bandwidth-bound operators of the YOLOv2 datapath: layout converters, 2x2 max-pool
+// (hls/core/core_compute.cpp:266-305), the HLS reorg tile (:354-379), and the three operators
+// the reference driver runs on the host CPU - input quantiser (yolo2_model.cpp:257-273),
+// flat-memory reorg + Q alignment (:112-129,358-401) and the region head (:406-425 +
+// src/core/yolo_region.cpp:123-141, src/core/yolo_math.cpp:19,226-250).
+// All are HBM-bound: every thread moves one 8/16-byte C4 pixel word or one coalesced planar row
+// element; nothing is re-read.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace y2 {
+
+namespace {
+
+template <typename T> struct Vec4;
+template <> struct Vec4<int16_t> { using type = uint2; };
+template <> struct Vec4<float> { using type = float4; };
+
+template <typename T> __device__ __forceinline__ T pool_floor();
+template <> __device__ __forceinline__ int16_t pool_floor<int16_t>() { return (int16_t)-32768; }   // core_io.cpp:96-99
+template <> __device__ __forceinline__ float pool_floor<float>() { return (float)(-1024 * 1024); }  // core_io.cpp:100-102
+
+template <typename T>
+__global__ void planar_to_c4_kernel(const T *__restrict__ src, T *__restrict__ dst, int B, int C, int H, int W,
+                                    long long sfs, long long dfs)
+{
+    const int G = ceil_div(C, 4), Wa = align8(W);
+    const long long total = (long long)B * G * H * W;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int x = idx % W;
+    long long r = idx / W;
+    int y = r % H; r /= H;
+    int g = r % G;
+    int f = r / G;
+    T v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        int c = g * 4 + t;
+        v[t] = (c < C) ? src[f * sfs + ((long long)c * H + y) * Wa + x] : (T)0;
+    }
+    T *d = dst + f * dfs + (((long long)g * H + y) * W + x) * 4;
+    *reinterpret_cast<typename Vec4<T>::type *>(d) = *reinterpret_cast<typename Vec4<T>::type *>(v);
+}
+
+template <typename T>
+__global__ void c4_to_planar_kernel(const T *__restrict__ src, T *__restrict__ dst, int B, int C, int H, int W,
+                                    long long sfs, long long dfs)
+{
+    const int G = ceil_div(C, 4), Wa = align8(W);
+    const long long total = (long long)B * G * H * W;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int x = idx % W;
+    long long r = idx / W;
+    int y = r % H; r /= H;
+    int g = r % G;
+    int f = r / G;
+    T v[4];
+    *reinterpret_cast<typename Vec4<T>::type *>(v) =
+        *reinterpret_cast<const typename Vec4<T>::type *>(src + f * sfs + (((long long)g * H + y) * W + x) * 4);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        int c = g * 4 + t;
+        if (c < C) dst[f * dfs + ((long long)c * H + y) * Wa + x] = v[t];
+    }
+}
+
+template <typename T>
+__global__ void maxpool_planar_kernel(const T *__restrict__ in, T *__restrict__ out, int ch, int ksize, int kstride,
+                                      int iw, int ih, int ow, int oh)
+{
+    const int iwa = align8(iw), owa = align8(ow);
+    const long long total = (long long)ch * oh * ow;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int x = idx % ow;
+    long long r = idx / ow;
+    int y = r % oh;
+    int c = r / oh;
+    T best = pool_floor<T>();
+    for (int i = 0; i < ksize; ++i)
+        for (int j = 0; j < ksize; ++j) {
+            int iy = y * kstride + i, ix = x * kstride + j;  // loader Padding forced to 0, core_scheduler.cpp:72-73
+            T v = (iy < ih && ix < iw) ? in[((long long)c * ih + iy) * iwa + ix] : pool_floor<T>();
+            if (v > best) best = v;
+        }
+    out[((long long)c * oh + y) * owa + x] = best;
+}
+
+template <typename T>
+__global__ void maxpool_c4_kernel(const T *__restrict__ in, T *__restrict__ out, int B, int G, int kstride, int iw,
+                                  int ih, int ow, int oh, long long ifs, long long ofs)
+{
+    const long long total = (long long)B * G * oh * ow;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int x = idx % ow;
+    long long r = idx / ow;
+    int y = r % oh; r /= oh;
+    int g = r % G;
+    int f = r / G;
+    T best[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) best[t] = pool_floor<T>();
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            int iy = y * kstride + i, ix = x * kstride + j;
+            if (iy < ih && ix < iw) {
+                T v[4];
+                *reinterpret_cast<typename Vec4<T>::type *>(v) = *reinterpret_cast<const typename Vec4<T>::type *>(
+                    in + f * ifs + (((long long)g * ih + iy) * iw + ix) * 4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (v[t] > best[t]) best[t] = v[t];
+            }
+        }
+    *reinterpret_cast<typename Vec4<T>::type *>(out + f * ofs + (((long long)g * oh + y) * ow + x) * 4) =
+        *reinterpret_cast<typename Vec4<T>::type *>(best);
+}
+
+// LayerType 2: out[m+2ky+kx][y][x] = in[m][2y+ky][2x+kx] for m stepping by TM (core_compute.cpp:354-379,
+// core_scheduler.cpp:88-112, yolo2_accel.cpp:127-169).
+template <typename T>
+__global__ void reorg_hls_planar_kernel(const T *__restrict__ in, T *__restrict__ out, int ch, int TM, int iw, int ih,
+                                        int ow, int oh)
+{
+    const int iwa = align8(iw), owa = align8(ow);
+    const long long total = (long long)ch * oh * ow;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int x = idx % ow;
+    long long r = idx / ow;
+    int y = r % oh;
+    int oc = r / oh;
+    int m = (oc / TM) * TM, q = oc - m;
+    if (q >= 4) return;  // only four phases exist; further tile channels are never written
+    int ky = q >> 1, kx = q & 1;
+    int iy = 2 * y + ky, ix = 2 * x + kx;
+    T v = (iy < ih && ix < iw) ? in[((long long)m * ih + iy) * iwa + ix] : (T)0;
+    out[((long long)oc * oh + y) * owa + x] = v;
+}
+
+__device__ __forceinline__ int16_t quantize_one(float in, float scale)
+{
+    float v = in * scale;  // yolo2_model.cpp:265-271
+    if (v > 32767.f) v = 32767.f;
+    if (v < -32768.f) v = -32768.f;
+    long long q = llroundf(v);  // round half away from zero
+    if (q > 32767) q = 32767;
+    if (q < -32768) q = -32768;
+    return (int16_t)q;
+}
+
+__global__ void quantize_kernel(const float *__restrict__ in, int16_t *__restrict__ out, size_t count, float scale)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < count) out[idx] = quantize_one(in[idx], scale);
+}
+
+template <typename T>
+__global__ void frames_to_c4_kernel(const float *__restrict__ frames, T *__restrict__ dst, int B, int C, int H, int W,
+                                    long long dfs, float scale)
+{
+    const int G = ceil_div(C, 4);
+    const long long total = (long long)B * G * H * W;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int x = idx % W;
+    long long r = idx / W;
+    int y = r % H; r /= H;
+    int g = r % G;
+    int f = r / G;
+    T v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        int c = g * 4 + t;
+        float s = (c < C) ? frames[(((long long)f * C + c) * H + y) * W + x] : 0.0f;
+        if constexpr (sizeof(T) == 2) v[t] = (c < C) ? quantize_one(s, scale) : (int16_t)0;
+        else v[t] = s;
+    }
+    *reinterpret_cast<typename Vec4<T>::type *>(dst + f * dfs + (((long long)g * H + y) * W + x) * 4) =
+        *reinterpret_cast<typename Vec4<T>::type *>(v);
+}
+
+// Source coordinates of the flat-memory reorg (yolo2_model.cpp:112-129 called as
+// reorg_cpu(x, W, H*C/4, 4, 2, out), :373): compact output flat index f -> compact source index.
+__device__ __forceinline__ void reorg_src(long long f, int c, int h, int w, int &cs, int &ys, int &xs)
+{
+    const long long hc = (long long)h * c / 4;
+    long long i = f % w, jj = f / w, j = jj % hc, k = jj / hc;
+    long long s = (2 * i + (k & 1)) + 2LL * w * (2 * j + (k >> 1));
+    xs = (int)(s % w);
+    long long row = s / w;
+    ys = (int)(row % h);
+    cs = (int)(row / h);
+}
+
+template <typename T> __device__ __forceinline__ T reorg_shift(T v, int shift);
+template <> __device__ __forceinline__ int16_t reorg_shift<int16_t>(int16_t v, int shift)
+{
+    int t = (int)v;
+    if (shift > 0) t >>= shift;  // arithmetic, no rounding (yolo2_model.cpp:386-391)
+    return (int16_t)t;
+}
+template <> __device__ __forceinline__ float reorg_shift<float>(float v, int) { return v; }
+
+template <typename T>
+__global__ void reorg_driver_planar_kernel(const T *__restrict__ in, T *__restrict__ out, int c, int h, int w, int shift)
+{
+    const int ow = w / 2, oh = h / 2, owa = align8(ow), wa = align8(w);
+    const long long total = (long long)4 * c * oh * owa;  // includes pad columns, which are zeroed (:375)
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int x = idx % owa;
+    long long row = idx / owa;
+    if (x >= ow) { out[idx] = (T)0; return; }
+    long long f = row * ow + x;
+    int cs, ys, xs;
+    reorg_src(f, c, h, w, cs, ys, xs);
+    out[idx] = reorg_shift<T>(in[((long long)cs * h + ys) * wa + xs], shift);
+}
+
+template <typename T>
+__global__ void reorg_driver_c4_kernel(const T *__restrict__ in, T *__restrict__ out, int B, int c, int h, int w,
+                                       int shift, long long ifs, long long ofs)
+{
+    const int ow = w / 2, oh = h / 2, OG = c;  // 4c output channels = c output groups
+    const long long total = (long long)B * OG * oh * ow;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int x = idx % ow;
+    long long r = idx / ow;
+    int y = r % oh; r /= oh;
+    int g = r % OG;
+    int f = r / OG;
+    T v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        int oc = g * 4 + t;
+        long long fl = ((long long)oc * oh + y) * ow + x;
+        int cs, ys, xs;
+        reorg_src(fl, c, h, w, cs, ys, xs);
+        v[t] = reorg_shift<T>(in[f * ifs + (((long long)(cs >> 2) * h + ys) * w + xs) * 4 + (cs & 3)], shift);
+    }
+    *reinterpret_cast<typename Vec4<T>::type *>(out + f * ofs + (((long long)g * oh + y) * ow + x) * 4) =
+        *reinterpret_cast<typename Vec4<T>::type *>(v);
+}
+
+__device__ __forceinline__ float logistic_ref(float x) { return (float)(1. / (1. + exp((double)(-x)))); }  // yolo_math.cpp:19
+
+// One thread per (frame, anchor, cell): strip + dequantise + logistic(x,y,obj) + class softmax.
+template <typename T, int LAYOUT>
+__global__ void region_kernel(const T *__restrict__ in, float *__restrict__ out, int B, int w, int h, int n, int classes,
+                              int coords, int softmax, int background, float scale, long long ifs)
+{
+    const int wh = w * h, per = coords + 1 + classes, wa = align8(w);
+    const long long total = (long long)B * n * wh;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int loc = idx % wh;
+    long long r = idx / wh;
+    int a = r % n;
+    int f = r / n;
+    int y = loc / w, x = loc - y * w;
+
+    auto fetch = [&](int e) -> float {
+        int ch = a * per + e;
+        T v;
+        if (LAYOUT == 0) v = in[f * ifs + ((long long)ch * h + y) * wa + x];
+        else v = in[f * ifs + (((long long)(ch >> 2) * h + y) * w + x) * 4 + (ch & 3)];
+        if (sizeof(T) == 2) return (float)v * scale;  // yolo2_model.cpp:416-420
+        return (float)v;
+    };
+    float *o = out + ((long long)f * n + a) * per * wh + loc;
+    for (int e = 0; e < coords; ++e) {
+        float v = fetch(e);
+        o[(long long)e * wh] = (e < 2) ? logistic_ref(v) : v;  // yolo_region.cpp:129-130
+    }
+    {
+        float v = fetch(coords);
+        o[(long long)coords * wh] = background ? v : logistic_ref(v);  // :131-132
+    }
+    const int first = coords + !background, nc = classes + background;
+    if (softmax) {  // yolo_math.cpp:226-241 with temp = 1, stride = w*h
+        float largest = -FLT_MAX;
+        for (int i = 0; i < nc; ++i) {
+            float v = fetch(first + i);
+            if (v > largest) largest = v;
+        }
+        float sum = 0;
+        for (int i = 0; i < nc; ++i) {
+            float arg = __fsub_rn(__fdiv_rn(fetch(first + i), 1.0f), __fdiv_rn(largest, 1.0f));
+            float e = (float)exp((double)arg);
+            sum = __fadd_rn(sum, e);
+            o[(long long)(first + i) * wh] = e;
+        }
+        for (int i = 0; i < nc; ++i) o[(long long)(first + i) * wh] = __fdiv_rn(o[(long long)(first + i) * wh], sum);
+    } else {
+        for (int i = 0; i < nc; ++i) o[(long long)(first + i) * wh] = fetch(first + i);  // raw copy (yolo_region.cpp:125)
+    }
+}
+
+inline unsigned blocks_for(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+}  // namespace
+
+void launch_planar_to_c4(const void *src, void *dst, int B, int C, int H, int W, long long sfs, long long dfs,
+                         int elem_bytes, cudaStream_t st)
+{
+    long long total = (long long)B * ceil_div(C, 4) * H * W;
+    if (elem_bytes == 2)
+        planar_to_c4_kernel<int16_t><<<blocks_for(total, 256), 256, 0, st>>>((const int16_t *)src, (int16_t *)dst, B, C, H, W, sfs, dfs);
+    else
+        planar_to_c4_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float *)src, (float *)dst, B, C, H, W, sfs, dfs);
+}
+
+void launch_c4_to_planar(const void *src, void *dst, int B, int C, int H, int W, long long sfs, long long dfs,
+                         int elem_bytes, cudaStream_t st)
+{
+    long long total = (long long)B * ceil_div(C, 4) * H * W;
+    if (elem_bytes == 2)
+        c4_to_planar_kernel<int16_t><<<blocks_for(total, 256), 256, 0, st>>>((const int16_t *)src, (int16_t *)dst, B, C, H, W, sfs, dfs);
+    else
+        c4_to_planar_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float *)src, (float *)dst, B, C, H, W, sfs, dfs);
+}
+
+void launch_maxpool_planar(const void *in, void *out, int ch, int ksize, int kstride, int iw, int ih, int ow, int oh,
+                           int elem_bytes, cudaStream_t st)
+{
+    long long total = (long long)ch * oh * ow;
+    if (elem_bytes == 2)
+        maxpool_planar_kernel<int16_t><<<blocks_for(total, 256), 256, 0, st>>>((const int16_t *)in, (int16_t *)out, ch, ksize, kstride, iw, ih, ow, oh);
+    else
+        maxpool_planar_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float *)in, (float *)out, ch, ksize, kstride, iw, ih, ow, oh);
+}
+
+void launch_maxpool_c4(const void *in, void *out, int B, int G, int kstride, int iw, int ih, int ow, int oh,
+                       long long ifs, long long ofs, int elem_bytes, cudaStream_t st)
+{
+    long long total = (long long)B * G * oh * ow;
+    if (elem_bytes == 2)
+        maxpool_c4_kernel<int16_t><<<blocks_for(total, 256), 256, 0, st>>>((const int16_t *)in, (int16_t *)out, B, G, kstride, iw, ih, ow, oh, ifs, ofs);
+    else
+        maxpool_c4_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float *)in, (float *)out, B, G, kstride, iw, ih, ow, oh, ifs, ofs);
+}
+
+void launch_reorg_hls_planar(const void *in, void *out, int ch, int TM, int iw, int ih, int ow, int oh, int elem_bytes,
+                             cudaStream_t st)
+{
+    long long total = (long long)ch * oh * ow;
+    if (elem_bytes == 2)
+        reorg_hls_planar_kernel<int16_t><<<blocks_for(total, 256), 256, 0, st>>>((const int16_t *)in, (int16_t *)out, ch, TM, iw, ih, ow, oh);
+    else
+        reorg_hls_planar_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float *)in, (float *)out, ch, TM, iw, ih, ow, oh);
+}
+
+void launch_quantize(const float *in, int16_t *out, size_t count, int q_in, cudaStream_t st)
+{
+    quantize_kernel<<<blocks_for((long long)count, 256), 256, 0, st>>>(in, out, count, ldexpf(1.0f, q_in));
+}
+
+void launch_frames_to_c4(const float *frames, void *dst, int B, int C, int H, int W, long long dfs, int q_in,
+                         int elem_bytes, cudaStream_t st)
+{
+    long long total = (long long)B * ceil_div(C, 4) * H * W;
+    if (elem_bytes == 2)
+        frames_to_c4_kernel<int16_t><<<blocks_for(total, 256), 256, 0, st>>>(frames, (int16_t *)dst, B, C, H, W, dfs, ldexpf(1.0f, q_in));
+    else
+        frames_to_c4_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>(frames, (float *)dst, B, C, H, W, dfs, 1.0f);
+}
+
+void launch_reorg_driver_planar(const void *in, void *out, int c, int h, int w, int shift, int elem_bytes, cudaStream_t st)
+{
+    long long total = (long long)4 * c * (h / 2) * align8(w / 2);
+    if (elem_bytes == 2)
+        reorg_driver_planar_kernel<int16_t><<<blocks_for(total, 256), 256, 0, st>>>((const int16_t *)in, (int16_t *)out, c, h, w, shift);
+    else
+        reorg_driver_planar_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float *)in, (float *)out, c, h, w, shift);
+}
+
+void launch_reorg_driver_c4(const void *in, void *out, int B, int c, int h, int w, int shift, long long ifs,
+                            long long ofs, int elem_bytes, cudaStream_t st)
+{
+    long long total = (long long)B * c * (h / 2) * (w / 2);
+    if (elem_bytes == 2)
+        reorg_driver_c4_kernel<int16_t><<<blocks_for(total, 256), 256, 0, st>>>((const int16_t *)in, (int16_t *)out, B, c, h, w, shift, ifs, ofs);
+    else
+        reorg_driver_c4_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float *)in, (float *)out, B, c, h, w, shift, ifs, ofs);
+}
+
+void launch_region(const void *in, float *out, int B, int w, int h, int n, int classes, int coords, int softmax,
+                   int background, int q, int layout, long long ifs, int elem_bytes, cudaStream_t st)
+{
+    long long total = (long long)B * n * w * h;
+    const float scale = ldexpf(1.0f, -q);
+    unsigned nb = blocks_for(total, 128);
+    if (elem_bytes == 2) {
+        if (layout == 0) region_kernel<int16_t, 0><<<nb, 128, 0, st>>>((const int16_t *)in, out, B, w, h, n, classes, coords, softmax, background, scale, ifs);
+        else region_kernel<int16_t, 1><<<nb, 128, 0, st>>>((const int16_t *)in, out, B, w, h, n, classes, coords, softmax, background, scale, ifs);
+    } else {
+        if (layout == 0) region_kernel<float, 0><<<nb, 128, 0, st>>>((const float *)in, out, B, w, h, n, classes, coords, softmax, background, 1.0f, ifs);
+        else region_kernel<float, 1><<<nb, 128, 0, st>>>((const float *)in, out, B, w, h, n, classes, coords, softmax, background, 1.0f, ifs);
+    }
+}
+
+}  // namespace y2

@@ -1,0 +1,813 @@
+// C ABI of the B200 YOLOv2 datapath (include/yolo2cuda.h): context, the YOLO2_FPGA drop-in
+// (yolo2cuda_layer_*), the driver-side operators and the whole-network executor that replaces
+// yolov2_hls_ps (hls/models/yolov2/yolo2_model.cpp:229-449).  No CPU fallback anywhere: every
+// compute entry needs a CUDA device and fails with a YOLO2CUDA_* code otherwise.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/yolo2cuda.h"
+#include "common.cuh"
+
+using namespace y2;
+
+struct yolo2cuda_ctx {
+    int device = 0;
+    int precision = 16;
+    int elem = 2;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err = "ok";
+    uint64_t launches = 0;
+    const char *last_kernel = "";
+    int force_generic = 0;
+    // growable device scratch for the per-layer entry points
+    struct Scratch { void *p = nullptr; size_t bytes = 0; } s_in, s_out, s_w, s_b, s_c4in, s_c4out, s_wprep;
+};
+
+namespace {
+
+int fail(yolo2cuda_ctx *ctx, int code, const char *fmt, ...)
+{
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+#define CUDA_OK(ctx, call)                                                                            \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? YOLO2CUDA_MEMORY_ERROR : YOLO2CUDA_LAUNCH_ERROR, \
+                        "%s failed: %s", #call, cudaGetErrorString(e_));                              \
+    } while (0)
+
+int ensure(yolo2cuda_ctx *ctx, yolo2cuda_ctx::Scratch &s, size_t bytes)
+{
+    if (s.bytes >= bytes) return YOLO2CUDA_SUCCESS;
+    if (s.p) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(s.p);
+        s.p = nullptr;
+        s.bytes = 0;
+    }
+    size_t want = bytes + (bytes >> 2) + 4096;
+    CUDA_OK(ctx, cudaMalloc(&s.p, want));
+    s.bytes = want;
+    return YOLO2CUDA_SUCCESS;
+}
+
+size_t planar_elems(int c, int h, int w) { return (size_t)c * h * align8(w); }
+size_t c4_elems(int c, int h, int w) { return (size_t)ceil_div(c, 4) * h * w * 4; }
+
+// The checks of yolo2_accel.cpp:75-87 (and the board driver's validate_conv_params,
+// linux_app/src/yolo2_accel_linux.c:383-414), returned as an error instead of assert().
+const char *validate_layer_args(int IFM, int OFM, int K, int S, int Iw, int Ih, int Ow, int Oh, int Pad, int TM, int TN,
+                                int TR, int TC, int bound, int mLxTM, int mLa1xTM, int type)
+{
+    if (OFM <= 0 || OFM > 2048) return "OFM_num out of (0,2048]";
+    if (IFM <= 0 || IFM > 2048) return "IFM_num out of (0,2048]";
+    if (S <= 0 || S > 2) return "Kstride out of (0,2]";
+    if (K <= 0 || K > 3) return "Ksize out of (0,3]";
+    if (Iw <= 0 || Iw > 1024 || Ih <= 0 || Ih > 1024) return "input dims out of (0,1024]";
+    if (Ow <= 0 || Ow > 1024 || Oh <= 0 || Oh > 1024) return "output dims out of (0,1024]";
+    if (Pad < 0 || Pad > 4) return "Padding out of [0,4]";
+    if (TM <= 0 || TM > YOLO2CUDA_Tm) return "TM out of (0,Tm]";
+    if (TN < 0 || TN > YOLO2CUDA_Tn) return "TN out of [0,Tn]";
+    if (TR <= 0 || TR > YOLO2CUDA_Tr) return "TR out of (0,Tr]";
+    if (TC <= 0 || TC > YOLO2CUDA_Tc) return "TC out of (0,Tc]";
+    if (type < 0 || type > 2) return "LayerType must be 0, 1 or 2";
+    // software-pipeline drain bounds (yolo2_accel.cpp:136-146): the only values for which the
+    // reference writes every output tile exactly once
+    const int mLoops = ceil_div(OFM, TM);
+    if (mLxTM != mLoops * TM) return "mLoopsxTM != ceil(OFM/TM)*TM";
+    if (type == 0) {
+        if (bound != (mLoops + 1) * TM) return "OFM_num_bound != (mLoops+1)*TM for conv";
+        if (TN <= 0) return "TN must be > 0 for conv";
+    } else {
+        if (bound != (mLoops + 2) * TM) return "OFM_num_bound != (mLoops+2)*TM for pool/reorg";
+        if (mLa1xTM != (mLoops + 1) * TM) return "mLoops_a1xTM != (mLoops+1)*TM for pool/reorg";
+    }
+    return nullptr;
+}
+
+bool fast_shift_ok(int so) { return so >= 8; }  // effective shift = min(so,30), see conv_i16.cu
+
+int run_conv_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, const void *Weight, const void *Beta,
+                       int IFM, int OFM, int K, int S, int Iw, int Ih, int Ow, int Oh, int Pad, int IsNL, int TM,
+                       int TN, int Qw, int Qa_in, int Qa_out, int Qb)
+{
+    cudaStream_t st = ctx->stream;
+    const int so = Qa_in + Qw - Qa_out, sb = Qb - Qa_out;
+    bool fast = !ctx->force_generic && (K == 1 || K == 3) && S == 1 && Pad == K / 2 && Ow == Iw && Oh == Ih &&
+                (TN == 4 || IFM <= TN);
+    if (ctx->elem == 2) fast = fast && fast_shift_ok(so);
+    ConvFastParams p{};
+    if (fast) {
+        p.B = 1; p.H = Ih; p.W = Iw; p.G = ceil_div(IFM, 4); p.OFM = OFM;
+        if (conv_fast_plan(p, K, ctx->elem) == 0) fast = false;
+    }
+    if (!fast) {
+        ctx->last_kernel = ctx->elem == 2 ? "conv_i16_generic" : "conv_f32_generic";
+        if (ctx->elem == 2)
+            launch_conv_i16_generic((const int16_t *)Input, (int16_t *)Output, (const int16_t *)Weight,
+                                    (const int16_t *)Beta, IFM, OFM, K, S, Iw, Ih, Ow, Oh, Pad, IsNL, TM, TN, so, sb, st);
+        else
+            launch_conv_f32_generic((const float *)Input, (float *)Output, (const float *)Weight, (const float *)Beta,
+                                    IFM, OFM, K, S, Iw, Ih, Ow, Oh, Pad, IsNL, TM, TN, st);
+        ctx->launches += 1;
+        CUDA_OK(ctx, cudaGetLastError());
+        return YOLO2CUDA_SUCCESS;
+    }
+    int rc;
+    if ((rc = ensure(ctx, ctx->s_c4in, c4_elems(IFM, Ih, Iw) * ctx->elem))) return rc;
+    if ((rc = ensure(ctx, ctx->s_c4out, c4_elems(OFM, Oh, Ow) * ctx->elem))) return rc;
+    if ((rc = ensure(ctx, ctx->s_wprep, wprep_bytes(IFM, OFM, K, ctx->elem)))) return rc;
+    launch_planar_to_c4(Input, ctx->s_c4in.p, 1, IFM, Ih, Iw, 0, 0, ctx->elem, st);
+    if (ctx->elem == 2) launch_wprep_i16((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, st);
+    else launch_wprep_f32((const float *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, st);
+    p.in = ctx->s_c4in.p; p.out = ctx->s_c4out.p; p.w = ctx->s_wprep.p; p.bias = Beta;
+    p.in_frame_stride = 0; p.out_frame_stride = 0;
+    p.so = so > 30 ? 30 : so; p.sb = sb; p.leaky = IsNL;
+    int n = ctx->elem == 2 ? launch_conv_i16_fast(p, K, st, &ctx->last_kernel) : launch_conv_f32_fast(p, K, st, &ctx->last_kernel);
+    if (n < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "no fast conv variant for TP=%d K=%d", p.TP, K);
+    launch_c4_to_planar(ctx->s_c4out.p, Output, 1, OFM, Oh, Ow, 0, 0, ctx->elem, st);
+    ctx->launches += 3 + n;
+    CUDA_OK(ctx, cudaGetLastError());
+    return YOLO2CUDA_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yolo2cuda_create(yolo2cuda_ctx **out, int device, int precision)
+{
+    if (!out) return YOLO2CUDA_ERROR;
+    *out = nullptr;
+    if (precision != YOLO2CUDA_PRECISION_INT16 && precision != YOLO2CUDA_PRECISION_FP32) return YOLO2CUDA_ERROR;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return YOLO2CUDA_INIT_ERROR;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return YOLO2CUDA_INIT_ERROR;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return YOLO2CUDA_INIT_ERROR;
+    if (prop.major != 10) {
+        fprintf(stderr, "yolo2cuda: device %d is sm_%d%d; this library contains sm_100a code only\n", device, prop.major, prop.minor);
+        return YOLO2CUDA_INIT_ERROR;
+    }
+    yolo2cuda_ctx *ctx = new yolo2cuda_ctx();
+    ctx->device = device;
+    ctx->precision = precision;
+    ctx->elem = precision == YOLO2CUDA_PRECISION_INT16 ? 2 : 4;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return YOLO2CUDA_INIT_ERROR;
+    }
+    ctx->stream = ctx->own_stream;
+    const char *fg = getenv("YOLO2CUDA_FORCE_GENERIC");
+    ctx->force_generic = (fg && fg[0] && fg[0] != '0') ? 1 : 0;
+    *out = ctx;
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_destroy(yolo2cuda_ctx *ctx)
+{
+    if (!ctx) return YOLO2CUDA_ERROR;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    yolo2cuda_ctx::Scratch *all[] = {&ctx->s_in, &ctx->s_out, &ctx->s_w, &ctx->s_b, &ctx->s_c4in, &ctx->s_c4out, &ctx->s_wprep};
+    for (auto *s : all)
+        if (s->p) cudaFree(s->p);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_set_stream(yolo2cuda_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return YOLO2CUDA_ERROR;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_synchronize(yolo2cuda_ctx *ctx)
+{
+    if (!ctx) return YOLO2CUDA_ERROR;
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return YOLO2CUDA_SUCCESS;
+}
+
+const char *yolo2cuda_last_error(const yolo2cuda_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t yolo2cuda_launch_count(const yolo2cuda_ctx *ctx) { return ctx ? ctx->launches : 0; }
+const char *yolo2cuda_last_kernel(const yolo2cuda_ctx *ctx) { return ctx ? ctx->last_kernel : ""; }
+
+int yolo2cuda_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, const void *Weight, const void *Beta,
+                        int IFM_num, int OFM_num, int Ksize, int Kstride, int Input_w, int Input_h, int Output_w,
+                        int Output_h, int Padding, int IsNL, int IsBN, int TM, int TN, int TR, int TC,
+                        int OFM_num_bound, int mLoopsxTM, int mLoops_a1xTM, int LayerType, int Qw, int Qa_in,
+                        int Qa_out, int Qb)
+{
+    (void)IsBN;  // unused by the reference too (BN is pre-folded, yolo2_accel.cpp:27)
+    if (!ctx) return YOLO2CUDA_ERROR;
+    if (!Input || !Output) return fail(ctx, YOLO2CUDA_ERROR, "Input/Output must not be NULL");
+    const char *why = validate_layer_args(IFM_num, OFM_num, Ksize, Kstride, Input_w, Input_h, Output_w, Output_h, Padding,
+                                          TM, TN, TR, TC, OFM_num_bound, mLoopsxTM, mLoops_a1xTM, LayerType);
+    if (why) return fail(ctx, YOLO2CUDA_ERROR, "invalid layer arguments: %s", why);
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (LayerType == YOLO2CUDA_LAYER_CONV) {
+        if (!Weight || !Beta) return fail(ctx, YOLO2CUDA_ERROR, "conv needs Weight and Beta");
+        // every output pixel must read inside the zero-padded input (core_io.cpp:53-70 pads, never wraps)
+        return run_conv_layer_dev(ctx, Input, Output, Weight, Beta, IFM_num, OFM_num, Ksize, Kstride, Input_w, Input_h,
+                                  Output_w, Output_h, Padding, IsNL, TM, TN, Qw, Qa_in, Qa_out, Qb);
+    }
+    if (LayerType == YOLO2CUDA_LAYER_MAXPOOL) {
+        // the reference store is hard-wired to window position (1,1): only 2x2 windows are defined (core_compute.cpp:299-300)
+        if (Ksize != 2) return fail(ctx, YOLO2CUDA_ERROR, "maxpool supports Ksize==2 only (reference store is hard-wired)");
+        launch_maxpool_planar(Input, Output, OFM_num, Ksize, Kstride, Input_w, Input_h, Output_w, Output_h, ctx->elem, st);
+        ctx->last_kernel = "maxpool_planar";
+    } else {
+        launch_reorg_hls_planar(Input, Output, OFM_num, TM, Input_w, Input_h, Output_w, Output_h, ctx->elem, st);
+        ctx->last_kernel = "reorg_hls_planar";
+    }
+    ctx->launches += 1;
+    CUDA_OK(ctx, cudaGetLastError());
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_layer_host(yolo2cuda_ctx *ctx, const void *Input, void *Output, const void *Weight, const void *Beta,
+                         int IFM_num, int OFM_num, int Ksize, int Kstride, int Input_w, int Input_h, int Output_w,
+                         int Output_h, int Padding, int IsNL, int IsBN, int TM, int TN, int TR, int TC,
+                         int OFM_num_bound, int mLoopsxTM, int mLoops_a1xTM, int LayerType, int Qw, int Qa_in,
+                         int Qa_out, int Qb)
+{
+    if (!ctx) return YOLO2CUDA_ERROR;
+    if (!Input || !Output) return fail(ctx, YOLO2CUDA_ERROR, "Input/Output must not be NULL");
+    const char *why = validate_layer_args(IFM_num, OFM_num, Ksize, Kstride, Input_w, Input_h, Output_w, Output_h, Padding,
+                                          TM, TN, TR, TC, OFM_num_bound, mLoopsxTM, mLoops_a1xTM, LayerType);
+    if (why) return fail(ctx, YOLO2CUDA_ERROR, "invalid layer arguments: %s", why);
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t e = ctx->elem;
+    const size_t in_b = planar_elems(IFM_num, Input_h, Input_w) * e, out_b = planar_elems(OFM_num, Output_h, Output_w) * e;
+    int rc;
+    if ((rc = ensure(ctx, ctx->s_in, in_b))) return rc;
+    if ((rc = ensure(ctx, ctx->s_out, out_b))) return rc;
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->s_in.p, Input, in_b, cudaMemcpyHostToDevice, st));
+    // pad columns W..ceil8(W)-1 of Output are never written by the reference (core_compute.cpp:218-219):
+    // round-trip the caller's buffer so they keep their values
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->s_out.p, Output, out_b, cudaMemcpyHostToDevice, st));
+    const void *dW = nullptr, *dB = nullptr;
+    if (LayerType == YOLO2CUDA_LAYER_CONV) {
+        if (!Weight || !Beta) return fail(ctx, YOLO2CUDA_ERROR, "conv needs Weight and Beta");
+        const size_t w_b = (size_t)IFM_num * OFM_num * Ksize * Ksize * e, b_b = (size_t)OFM_num * e;
+        if ((rc = ensure(ctx, ctx->s_w, w_b))) return rc;
+        if ((rc = ensure(ctx, ctx->s_b, b_b))) return rc;
+        CUDA_OK(ctx, cudaMemcpyAsync(ctx->s_w.p, Weight, w_b, cudaMemcpyHostToDevice, st));
+        CUDA_OK(ctx, cudaMemcpyAsync(ctx->s_b.p, Beta, b_b, cudaMemcpyHostToDevice, st));
+        dW = ctx->s_w.p;
+        dB = ctx->s_b.p;
+    }
+    rc = yolo2cuda_layer_dev(ctx, ctx->s_in.p, ctx->s_out.p, dW, dB, IFM_num, OFM_num, Ksize, Kstride, Input_w, Input_h,
+                             Output_w, Output_h, Padding, IsNL, IsBN, TM, TN, TR, TC, OFM_num_bound, mLoopsxTM,
+                             mLoops_a1xTM, LayerType, Qw, Qa_in, Qa_out, Qb);
+    if (rc) return rc;
+    CUDA_OK(ctx, cudaMemcpyAsync(Output, ctx->s_out.p, out_b, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_quantize_input_dev(yolo2cuda_ctx *ctx, const float *in, int16_t *out, size_t count, int q_in)
+{
+    if (!ctx || !in || !out) return YOLO2CUDA_ERROR;
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    launch_quantize(in, out, count, q_in, ctx->stream);
+    ctx->launches += 1;
+    CUDA_OK(ctx, cudaGetLastError());
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_reorg_dev(yolo2cuda_ctx *ctx, const void *in, void *out, int c, int h, int w, int shift)
+{
+    if (!ctx || !in || !out) return YOLO2CUDA_ERROR;
+    if (c <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1) || (((long long)h * c) & 3) || shift < 0 || shift > 31)
+        return fail(ctx, YOLO2CUDA_ERROR, "reorg needs even h,w, h*c divisible by 4 and 0<=shift<=31");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    launch_reorg_driver_planar(in, out, c, h, w, shift, ctx->elem, ctx->stream);
+    ctx->launches += 1;
+    CUDA_OK(ctx, cudaGetLastError());
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_region_dev(yolo2cuda_ctx *ctx, const void *in, float *out, int w, int h, int n, int classes, int coords,
+                         int softmax, int background, int q)
+{
+    if (!ctx || !in || !out) return YOLO2CUDA_ERROR;
+    if (w <= 0 || h <= 0 || n <= 0 || classes <= 0 || coords < 4) return fail(ctx, YOLO2CUDA_ERROR, "bad region dims");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    launch_region(in, out, 1, w, h, n, classes, coords, softmax, background, q, 0, 0, ctx->elem, ctx->stream);
+    ctx->launches += 1;
+    CUDA_OK(ctx, cudaGetLastError());
+    return YOLO2CUDA_SUCCESS;
+}
+
+}  // extern "C"
+
+// ================================ whole-network executor ========================================
+
+struct TensorView {
+    void *base = nullptr;          // frame 0, first group of this tensor
+    long long frame_stride = 0;    // elements between frames
+    int C = 0, H = 0, W = 0;
+};
+
+struct LayerPlan {
+    yolo2cuda_layer_desc d;
+    TensorView in, out;
+    bool fast = false;
+    ConvFastParams cp{};
+    int conv_index = -1;
+    size_t w_off = 0, b_off = 0;   // element offsets into the reference blobs
+    void *w_dev = nullptr;         // device weight layout (fast path)
+    int Qw = 0, Qa_in = 0, Qa_out = 0, Qb = 0;
+    int reorg_shift = 0;
+    int region_q = 0;
+    const char *variant = "";
+};
+
+struct yolo2cuda_net {
+    yolo2cuda_ctx *ctx = nullptr;
+    std::vector<LayerPlan> L;
+    int max_batch = 0;
+    int in_c = 0, in_h = 0, in_w = 0;
+    size_t region_outputs = 0;
+    std::vector<void *> owned;     // device allocations
+    void *d_input_c4 = nullptr;
+    void *d_frames = nullptr;      // staging for forward_host: float [max_batch][c][h][w]
+    void *d_region = nullptr;      // staging for forward_host
+    void *d_wblob = nullptr, *d_bblob = nullptr;
+    void *d_tmp_planar_in = nullptr, *d_tmp_planar_out = nullptr;  // generic-fallback / dump scratch
+    size_t tmp_planar_elems = 0;
+    bool weights_loaded = false;
+    int region_q = 0;
+    int input_q = 0;
+    uint64_t launches_per_forward = 0;
+    int last_batch = 0;
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<float> layer_ms;
+};
+
+namespace {
+
+int net_alloc(yolo2cuda_net *net, void **p, size_t bytes)
+{
+    yolo2cuda_ctx *ctx = net->ctx;
+    CUDA_OK(ctx, cudaMalloc(p, bytes ? bytes : 16));
+    CUDA_OK(ctx, cudaMemsetAsync(*p, 0, bytes ? bytes : 16, ctx->stream));
+    net->owned.push_back(*p);
+    return YOLO2CUDA_SUCCESS;
+}
+
+// Index of the conv whose output Q is remembered for the concat (the reference hard-codes
+// `i == 24`, yolo2_model.cpp:332-334): the non-reorg input of the first multi-input route that
+// has a reorg input.
+int find_skip_layer(const std::vector<LayerPlan> &L)
+{
+    for (size_t i = 0; i < L.size(); ++i)
+        if (L[i].d.type == YOLO2CUDA_ROUTE && L[i].d.n_inputs >= 2)
+            for (int a = 0; a < L[i].d.n_inputs; ++a)
+                if (L[L[i].d.inputs[a]].d.type == YOLO2CUDA_REORG)
+                    for (int b = 0; b < L[i].d.n_inputs; ++b)
+                        if (b != a) return L[i].d.inputs[b];
+    return -1;
+}
+
+int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *region_dev)
+{
+    yolo2cuda_ctx *ctx = net->ctx;
+    cudaStream_t st = ctx->stream;
+    const int e = ctx->elem;
+    uint64_t launches = 0;
+    const long long in_stride = (long long)c4_elems(net->in_c, net->in_h, net->in_w);
+    launch_frames_to_c4(frames_dev, net->d_input_c4, B, net->in_c, net->in_h, net->in_w, in_stride,
+                        net->input_q, e, st);
+    ++launches;
+    for (size_t i = 0; i < net->L.size(); ++i) {
+        LayerPlan &l = net->L[i];
+        if (net->timing) cudaEventRecord(net->ev[i], st);
+        switch (l.d.type) {
+        case YOLO2CUDA_CONV: {
+            if (l.fast) {
+                ConvFastParams p = l.cp;
+                p.B = B;
+                int n = e == 2 ? launch_conv_i16_fast(p, l.d.size, st, &l.variant) : launch_conv_f32_fast(p, l.d.size, st, &l.variant);
+                if (n < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "layer %zu: no fast conv variant", i);
+                launches += n;
+                ctx->last_kernel = l.variant;
+            } else {
+                // contract-complete fallback, one frame at a time through the planar kernels
+                const int TM = l.d.n < 32 ? l.d.n : 32, TN = l.d.c < 4 ? l.d.c : 4;
+                for (int f = 0; f < B; ++f) {
+                    launch_c4_to_planar((char *)l.in.base + (size_t)f * l.in.frame_stride * e, net->d_tmp_planar_in, 1, l.d.c,
+                                        l.d.h, l.d.w, 0, 0, e, st);
+                    if (e == 2)
+                        launch_conv_i16_generic((const int16_t *)net->d_tmp_planar_in, (int16_t *)net->d_tmp_planar_out,
+                                                (const int16_t *)net->d_wblob + l.w_off, (const int16_t *)net->d_bblob + l.b_off,
+                                                l.d.c, l.d.n, l.d.size, l.d.stride, l.d.w, l.d.h, l.d.out_w, l.d.out_h, l.d.pad,
+                                                l.d.leaky, TM, TN, l.Qa_in + l.Qw - l.Qa_out, l.Qb - l.Qa_out, st);
+                    else
+                        launch_conv_f32_generic((const float *)net->d_tmp_planar_in, (float *)net->d_tmp_planar_out,
+                                                (const float *)net->d_wblob + l.w_off, (const float *)net->d_bblob + l.b_off,
+                                                l.d.c, l.d.n, l.d.size, l.d.stride, l.d.w, l.d.h, l.d.out_w, l.d.out_h, l.d.pad,
+                                                l.d.leaky, TM, TN, st);
+                    launch_planar_to_c4(net->d_tmp_planar_out, (char *)l.out.base + (size_t)f * l.out.frame_stride * e, 1,
+                                        l.d.out_c, l.d.out_h, l.d.out_w, 0, 0, e, st);
+                    launches += 3;
+                }
+                ctx->last_kernel = e == 2 ? "conv_i16_generic" : "conv_f32_generic";
+            }
+            break;
+        }
+        case YOLO2CUDA_MAXPOOL:
+            launch_maxpool_c4(l.in.base, l.out.base, B, ceil_div(l.d.c, 4), l.d.stride, l.d.w, l.d.h, l.d.out_w, l.d.out_h,
+                              l.in.frame_stride, l.out.frame_stride, e, st);
+            ++launches;
+            break;
+        case YOLO2CUDA_REORG:
+            launch_reorg_driver_c4(l.in.base, l.out.base, B, l.d.c, l.d.h, l.d.w, l.reorg_shift, l.in.frame_stride,
+                                   l.out.frame_stride, e, st);
+            ++launches;
+            break;
+        case YOLO2CUDA_ROUTE:
+            break;  // no-op by placement, like the reference arena (yolo2_model.cpp:97-104,404-405)
+        case YOLO2CUDA_REGION:
+            launch_region(l.in.base, region_dev, B, l.d.w, l.d.h, l.d.n, l.d.classes, l.d.coords, l.d.softmax,
+                          l.d.background, l.region_q, 1, l.in.frame_stride, e, st);
+            ++launches;
+            break;
+        default:
+            return fail(ctx, YOLO2CUDA_ERROR, "layer %zu: unsupported type %d", i, l.d.type);
+        }
+    }
+    if (net->timing) cudaEventRecord(net->ev[net->L.size()], st);
+    CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += launches;
+    net->launches_per_forward = launches;
+    net->last_batch = B;
+    return YOLO2CUDA_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yolo2cuda_net_create(yolo2cuda_ctx *ctx, const yolo2cuda_layer_desc *layers, int n_layers, int max_batch,
+                         yolo2cuda_net **out)
+{
+    if (!ctx || !layers || n_layers <= 0 || max_batch <= 0 || !out) return YOLO2CUDA_ERROR;
+    *out = nullptr;
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const int e = ctx->elem;
+    yolo2cuda_net *net = new yolo2cuda_net();
+    net->ctx = ctx;
+    net->max_batch = max_batch;
+    net->L.resize(n_layers);
+    for (int i = 0; i < n_layers; ++i) net->L[i].d = layers[i];
+    net->in_c = layers[0].c; net->in_h = layers[0].h; net->in_w = layers[0].w;
+
+#define NET_FAIL(...)                                    \
+    do {                                                 \
+        int rc_ = fail(ctx, YOLO2CUDA_ERROR, __VA_ARGS__); \
+        yolo2cuda_net_destroy(net);                      \
+        return rc_;                                      \
+    } while (0)
+
+    // ---- validate the table -------------------------------------------------------------------
+    for (int i = 0; i < n_layers; ++i) {
+        const yolo2cuda_layer_desc &d = layers[i];
+        if (d.type == YOLO2CUDA_ROUTE) {
+            if (d.n_inputs < 1 || d.n_inputs > 4) NET_FAIL("layer %d: route needs 1..4 inputs", i);
+            for (int a = 0; a < d.n_inputs; ++a)
+                if (d.inputs[a] < 0 || d.inputs[a] >= i) NET_FAIL("layer %d: route input %d out of range", i, d.inputs[a]);
+        } else if (d.type == YOLO2CUDA_CONV) {
+            if (d.c <= 0 || d.n <= 0 || d.size <= 0 || d.size > 3 || d.stride <= 0 || d.stride > 2 || d.pad < 0 || d.pad > 4)
+                NET_FAIL("layer %d: conv parameters outside the accelerator contract", i);
+            if (d.out_c != d.n) NET_FAIL("layer %d: out_c != filters", i);
+        } else if (d.type == YOLO2CUDA_MAXPOOL) {
+            if (d.size != 2 || d.stride <= 0 || d.stride > 2) NET_FAIL("layer %d: maxpool must be 2x2, stride 1 or 2", i);
+        } else if (d.type == YOLO2CUDA_REORG) {
+            if (d.stride != 2 || (d.h & 1) || (d.w & 1) || (d.c & 3)) NET_FAIL("layer %d: reorg needs stride 2, even h,w and c%%4==0", i);
+        } else if (d.type == YOLO2CUDA_REGION) {
+            if (i != n_layers - 1) NET_FAIL("layer %d: region must be the last layer", i);
+            if (d.n * (d.coords + 1 + d.classes) != d.c) NET_FAIL("layer %d: region channel count mismatch", i);
+        } else {
+            NET_FAIL("layer %d: unknown type %d", i, d.type);
+        }
+    }
+
+    // ---- place tensors: concat inputs write straight into the concat buffer ---------------------
+    std::vector<int> concat_of(n_layers, -1), concat_goff(n_layers, 0);
+    for (int i = 0; i < n_layers; ++i) {
+        const yolo2cuda_layer_desc &d = layers[i];
+        if (d.type != YOLO2CUDA_ROUTE || d.n_inputs < 2) continue;
+        int goff = 0;
+        for (int a = 0; a < d.n_inputs; ++a) {
+            int s = d.inputs[a];
+            // resolve aliases (single-input routes) to the producing layer
+            while (layers[s].type == YOLO2CUDA_ROUTE && layers[s].n_inputs == 1) s = layers[s].inputs[0];
+            if (layers[s].type == YOLO2CUDA_ROUTE) NET_FAIL("layer %d: nested concat is not supported", i);
+            if (concat_of[s] >= 0) NET_FAIL("layer %d: tensor %d feeds two concats", i, s);
+            if (layers[s].out_c % 4) NET_FAIL("layer %d: concat input %d has out_c %% 4 != 0", i, s);
+            if (layers[s].out_h != d.out_h || layers[s].out_w != d.out_w) NET_FAIL("layer %d: concat input dims differ", i);
+            concat_of[s] = i;
+            concat_goff[s] = goff;
+            goff += layers[s].out_c / 4;
+        }
+        if (goff * 4 != d.out_c) NET_FAIL("layer %d: concat out_c mismatch", i);
+    }
+
+    int rc;
+    if ((rc = net_alloc(net, &net->d_input_c4, c4_elems(net->in_c, net->in_h, net->in_w) * (size_t)max_batch * e))) {
+        yolo2cuda_net_destroy(net);
+        return rc;
+    }
+    size_t max_planar = planar_elems(net->in_c, net->in_h, net->in_w);
+    std::vector<void *> concat_buf(n_layers, nullptr);
+    for (int i = 0; i < n_layers; ++i) {  // allocate concat buffers first
+        const yolo2cuda_layer_desc &d = layers[i];
+        if (d.type == YOLO2CUDA_ROUTE && d.n_inputs >= 2) {
+            if ((rc = net_alloc(net, &concat_buf[i], c4_elems(d.out_c, d.out_h, d.out_w) * (size_t)max_batch * e))) {
+                yolo2cuda_net_destroy(net);
+                return rc;
+            }
+        }
+    }
+    for (int i = 0; i < n_layers; ++i) {
+        LayerPlan &l = net->L[i];
+        const yolo2cuda_layer_desc &d = l.d;
+        // input view
+        if (i == 0) {
+            l.in.base = net->d_input_c4;
+            l.in.frame_stride = (long long)c4_elems(net->in_c, net->in_h, net->in_w);
+            l.in.C = net->in_c; l.in.H = net->in_h; l.in.W = net->in_w;
+        } else if (d.type != YOLO2CUDA_ROUTE) {
+            l.in = net->L[i - 1].out;
+            if (l.in.C != d.c || l.in.H != d.h || l.in.W != d.w)
+                NET_FAIL("layer %d: input dims %dx%dx%d do not match the previous output %dx%dx%d", i, d.c, d.h, d.w, l.in.C, l.in.H, l.in.W);
+        }
+        // output view
+        if (d.type == YOLO2CUDA_ROUTE) {
+            if (d.n_inputs == 1) {
+                l.out = net->L[d.inputs[0]].out;
+            } else {
+                l.out.base = concat_buf[i];
+                l.out.frame_stride = (long long)c4_elems(d.out_c, d.out_h, d.out_w);
+                l.out.C = d.out_c; l.out.H = d.out_h; l.out.W = d.out_w;
+            }
+        } else if (d.type == YOLO2CUDA_REGION) {
+            l.out = TensorView{};
+            net->region_outputs = (size_t)d.c * d.h * d.w;
+        } else {
+            l.out.C = d.out_c; l.out.H = d.out_h; l.out.W = d.out_w;
+            if (concat_of[i] >= 0) {
+                const yolo2cuda_layer_desc &cd = layers[concat_of[i]];
+                l.out.frame_stride = (long long)c4_elems(cd.out_c, cd.out_h, cd.out_w);
+                l.out.base = (char *)concat_buf[concat_of[i]] + (size_t)concat_goff[i] * d.out_h * d.out_w * 4 * e;
+            } else {
+                void *p = nullptr;
+                if ((rc = net_alloc(net, &p, c4_elems(d.out_c, d.out_h, d.out_w) * (size_t)max_batch * e))) {
+                    yolo2cuda_net_destroy(net);
+                    return rc;
+                }
+                l.out.base = p;
+                l.out.frame_stride = (long long)c4_elems(d.out_c, d.out_h, d.out_w);
+            }
+            max_planar = std::max(max_planar, planar_elems(d.out_c, d.out_h, d.out_w));
+        }
+        if (d.type == YOLO2CUDA_ROUTE) max_planar = std::max(max_planar, planar_elems(d.out_c, d.out_h, d.out_w));
+    }
+    net->tmp_planar_elems = max_planar;
+    if ((rc = net_alloc(net, &net->d_tmp_planar_in, max_planar * e)) || (rc = net_alloc(net, &net->d_tmp_planar_out, max_planar * e))) {
+        yolo2cuda_net_destroy(net);
+        return rc;
+    }
+    // weight blob offsets
+    size_t woff = 0, boff = 0;
+    int ci = 0;
+    for (int i = 0; i < n_layers; ++i) {
+        LayerPlan &l = net->L[i];
+        if (l.d.type != YOLO2CUDA_CONV) continue;
+        l.conv_index = ci++;
+        l.w_off = woff; l.b_off = boff;
+        woff += (size_t)l.d.c * l.d.n * l.d.size * l.d.size;
+        boff += (size_t)l.d.n;
+    }
+#undef NET_FAIL
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = net;
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_net_destroy(yolo2cuda_net *net)
+{
+    if (!net) return YOLO2CUDA_ERROR;
+    cudaSetDevice(net->ctx->device);
+    cudaStreamSynchronize(net->ctx->stream);
+    for (void *p : net->owned) cudaFree(p);
+    for (auto ev : net->ev) cudaEventDestroy(ev);
+    delete net;
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n_weights, const void *bias, size_t n_bias,
+                               const int32_t *weight_q, const int32_t *bias_q, int n_q, const int32_t *act_q, int n_act_q)
+{
+    if (!net || !weights || !bias) return YOLO2CUDA_ERROR;
+    yolo2cuda_ctx *ctx = net->ctx;
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const int e = ctx->elem;
+    cudaStream_t st = ctx->stream;
+    size_t need_w = 0, need_b = 0;
+    int n_conv = 0;
+    for (auto &l : net->L)
+        if (l.d.type == YOLO2CUDA_CONV) {
+            need_w += (size_t)l.d.c * l.d.n * l.d.size * l.d.size;
+            need_b += (size_t)l.d.n;
+            ++n_conv;
+        }
+    if (n_weights < need_w) return fail(ctx, YOLO2CUDA_ERROR, "weights file too small");  // yolo2_model.cpp:173,181
+    if (n_bias < need_b) return fail(ctx, YOLO2CUDA_ERROR, "bias file too small");
+    if (e == 2) {
+        if (!weight_q || !bias_q || n_q < n_conv) return fail(ctx, YOLO2CUDA_ERROR, "Q tables too small for conv layers");  // :186-188
+        if (!act_q || n_act_q <= 0) return fail(ctx, YOLO2CUDA_ERROR, "Activation Q table (iofm_Q.bin) is required for int16 inference.");  // :258-260
+    }
+    int rc;
+    if (!net->d_wblob) {
+        if ((rc = net_alloc(net, &net->d_wblob, need_w * e))) return rc;
+        if ((rc = net_alloc(net, &net->d_bblob, need_b * e))) return rc;
+    }
+    CUDA_OK(ctx, cudaMemcpyAsync(net->d_wblob, weights, need_w * e, cudaMemcpyHostToDevice, st));
+    CUDA_OK(ctx, cudaMemcpyAsync(net->d_bblob, bias, need_b * e, cudaMemcpyHostToDevice, st));
+
+    // ---- Q bookkeeping of the driver loop (yolo2_model.cpp:290-292, 311-336, 379-399, 416) ------
+    int current_qa = (e == 2) ? act_q[0] : 0, route_q = 0, pending_route_q = -1;
+    net->input_q = current_qa;  // yolo2_model.cpp:261
+    const int skip_layer = find_skip_layer(net->L);
+    for (size_t i = 0; i < net->L.size(); ++i) {
+        LayerPlan &l = net->L[i];
+        if (l.d.type == YOLO2CUDA_CONV) {
+            const int ci = l.conv_index;
+            if (e == 2) {
+                l.Qa_in = (ci < n_act_q) ? act_q[ci] : current_qa;
+                l.Qa_out = (ci + 1 < n_act_q) ? act_q[ci + 1] : l.Qa_in;
+                l.Qw = weight_q[ci];
+                l.Qb = bias_q[ci];
+                if (pending_route_q >= 0) l.Qa_in = pending_route_q;
+                current_qa = l.Qa_out;
+                if ((int)i == skip_layer) route_q = current_qa;
+                pending_route_q = -1;
+            }
+            const int so = l.Qa_in + l.Qw - l.Qa_out;
+            const int TM = l.d.n < 32 ? l.d.n : 32, TN = l.d.c < 4 ? l.d.c : 4;  // yolo2_model.cpp:307-308
+            l.fast = !ctx->force_generic && (l.d.size == 1 || l.d.size == 3) && l.d.stride == 1 && l.d.pad == l.d.size / 2 &&
+                     l.d.out_w == l.d.w && l.d.out_h == l.d.h && (e == 4 || fast_shift_ok(so));
+            if (l.fast) {
+                ConvFastParams p{};
+                p.B = net->max_batch; p.H = l.d.h; p.W = l.d.w; p.G = ceil_div(l.d.c, 4); p.OFM = l.d.n;
+                if (conv_fast_plan(p, l.d.size, e) == 0) l.fast = false;
+                else {
+                    if (!l.w_dev && (rc = net_alloc(net, &l.w_dev, wprep_bytes(l.d.c, l.d.n, l.d.size, e)))) return rc;
+                    if (e == 2) launch_wprep_i16((const int16_t *)net->d_wblob + l.w_off, l.w_dev, l.d.c, l.d.n, l.d.size, TM, TN, st);
+                    else launch_wprep_f32((const float *)net->d_wblob + l.w_off, l.w_dev, l.d.c, l.d.n, l.d.size, TM, TN, st);
+                    ctx->launches += 1;
+                    p.in = l.in.base; p.out = l.out.base; p.w = l.w_dev;
+                    p.bias = (char *)net->d_bblob + l.b_off * e;
+                    p.in_frame_stride = l.in.frame_stride; p.out_frame_stride = l.out.frame_stride;
+                    p.so = so > 30 ? 30 : so; p.sb = l.Qb - l.Qa_out; p.leaky = l.d.leaky;
+                    l.cp = p;
+                }
+            }
+        } else if (l.d.type == YOLO2CUDA_REORG) {
+            l.reorg_shift = 0;
+            if (e == 2 && route_q > 0) {
+                int target = route_q < current_qa ? route_q : current_qa;
+                l.reorg_shift = current_qa - target;
+                if (l.reorg_shift != 0) current_qa = target;
+                pending_route_q = current_qa;
+            }
+        } else if (l.d.type == YOLO2CUDA_REGION) {
+            l.region_q = current_qa;
+            net->region_q = current_qa;
+        }
+    }
+    CUDA_OK(ctx, cudaGetLastError());
+    CUDA_OK(ctx, cudaStreamSynchronize(st));
+    net->weights_loaded = true;
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_net_forward_dev(yolo2cuda_net *net, const float *frames, int batch, float *region_out)
+{
+    if (!net || !frames || !region_out || batch <= 0) return YOLO2CUDA_ERROR;
+    yolo2cuda_ctx *ctx = net->ctx;
+    if (!net->weights_loaded) return fail(ctx, YOLO2CUDA_ERROR, "weights not loaded");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const size_t frame_elems = (size_t)net->in_c * net->in_h * net->in_w;
+    for (int b0 = 0; b0 < batch; b0 += net->max_batch) {
+        int B = batch - b0 < net->max_batch ? batch - b0 : net->max_batch;
+        int rc = forward_chunk(net, frames + (size_t)b0 * frame_elems, B, region_out + (size_t)b0 * net->region_outputs);
+        if (rc) return rc;
+    }
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_net_forward_host(yolo2cuda_net *net, const float *frames, int batch, float *region_out)
+{
+    if (!net || !frames || !region_out || batch <= 0) return YOLO2CUDA_ERROR;
+    yolo2cuda_ctx *ctx = net->ctx;
+    if (!net->weights_loaded) return fail(ctx, YOLO2CUDA_ERROR, "weights not loaded");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t frame_elems = (size_t)net->in_c * net->in_h * net->in_w;
+    int rc;
+    if (!net->d_frames) {
+        if ((rc = net_alloc(net, &net->d_frames, frame_elems * net->max_batch * sizeof(float)))) return rc;
+        if ((rc = net_alloc(net, &net->d_region, net->region_outputs * net->max_batch * sizeof(float)))) return rc;
+    }
+    for (int b0 = 0; b0 < batch; b0 += net->max_batch) {
+        int B = batch - b0 < net->max_batch ? batch - b0 : net->max_batch;
+        CUDA_OK(ctx, cudaMemcpyAsync(net->d_frames, frames + (size_t)b0 * frame_elems, frame_elems * B * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+        if ((rc = forward_chunk(net, (const float *)net->d_frames, B, (float *)net->d_region))) return rc;
+        CUDA_OK(ctx, cudaMemcpyAsync(region_out + (size_t)b0 * net->region_outputs, net->d_region,
+                                     net->region_outputs * B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_net_get_layer_output(yolo2cuda_net *net, int layer, int frame, void *dst, size_t dst_elems)
+{
+    if (!net || !dst || layer < 0 || layer >= (int)net->L.size()) return YOLO2CUDA_ERROR;
+    yolo2cuda_ctx *ctx = net->ctx;
+    const LayerPlan &l = net->L[layer];
+    if (l.d.type == YOLO2CUDA_REGION) return fail(ctx, YOLO2CUDA_ERROR, "region output is returned by net_forward");
+    if (frame < 0 || frame >= net->last_batch) return fail(ctx, YOLO2CUDA_ERROR, "frame %d not in the last forward (batch %d)", frame, net->last_batch);
+    const size_t need = planar_elems(l.out.C, l.out.H, l.out.W);
+    if (dst_elems < need) return fail(ctx, YOLO2CUDA_ERROR, "dst too small: need %zu elements", need);
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const int e = ctx->elem;
+    cudaStream_t st = ctx->stream;
+    CUDA_OK(ctx, cudaMemsetAsync(net->d_tmp_planar_out, 0, need * e, st));
+    launch_c4_to_planar((char *)l.out.base + (size_t)frame * l.out.frame_stride * e, net->d_tmp_planar_out, 1, l.out.C, l.out.H,
+                        l.out.W, 0, 0, e, st);
+    ctx->launches += 1;
+    CUDA_OK(ctx, cudaMemcpyAsync(dst, net->d_tmp_planar_out, need * e, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_net_region_q(const yolo2cuda_net *net) { return net ? net->region_q : 0; }
+uint64_t yolo2cuda_net_launches_per_forward(const yolo2cuda_net *net) { return net ? net->launches_per_forward : 0; }
+int yolo2cuda_net_set_debug_keep(yolo2cuda_net *net, int keep)
+{
+    (void)keep;  // every layer owns its output buffer in this version: nothing to switch
+    return net ? YOLO2CUDA_SUCCESS : YOLO2CUDA_ERROR;
+}
+
+int yolo2cuda_net_layer_times(yolo2cuda_net *net, float *ms, int n_layers)
+{
+    if (!net || !ms) return YOLO2CUDA_ERROR;
+    yolo2cuda_ctx *ctx = net->ctx;
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (!net->timing) {
+        net->ev.resize(net->L.size() + 1);
+        for (auto &ev : net->ev) CUDA_OK(ctx, cudaEventCreate(&ev));
+        net->timing = true;
+        for (int i = 0; i < n_layers; ++i) ms[i] = -1.0f;
+        return YOLO2CUDA_SUCCESS;  // armed; numbers are available after the next forward
+    }
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n_layers && i < (int)net->L.size(); ++i) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, net->ev[i], net->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); t = -1.0f; }
+        ms[i] = t;
+    }
+    return YOLO2CUDA_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+"""Whole-network path: the `--backend cuda` replacement for yolov2_hls_ps.
+
+Reference interface: void yolov2_hls_ps(network*, const float* input, Precision)
+(hls/models/yolov2/yolo2_accel.hpp:21-23, defined yolo2_model.cpp:229-449): run every layer on
+the accelerator and leave the region tensor in net->layers[n-1].output.  Yolo2Net does the same
+for a batch of frames; yolov2_cuda_ps keeps the single-frame signature.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi, cfg as _cfg
+from .accel import Accelerator
+from .weights import WeightsPack
+
+
+class Yolo2Net:
+    def __init__(self, net: _cfg.Network, pack: WeightsPack, device: int = 0, max_batch: int = 32, accel: Accelerator = None):
+        self.net = net
+        self.precision = "int16" if pack.is_int16 else "fp32"
+        self.accel = accel or Accelerator(device, self.precision)
+        if self.accel.precision != self.precision:
+            raise _capi.Yolo2CudaError(_capi.ERROR, "context precision does not match the weight pack")
+        self.lib = self.accel.lib
+        self.max_batch = max_batch
+        self.handle = C.c_void_p()
+        self._descs = _cfg.to_desc_array(net)
+        _capi.check(self.accel.ctx, self.lib.yolo2cuda_net_create(self.accel.ctx, self._descs, len(net.layers), max_batch,
+                                                                  C.byref(self.handle)))
+        self.load_weights(pack)
+        last = net.layers[-1]
+        self.region_outputs = last.c * last.h * last.w
+
+    def load_weights(self, pack: WeightsPack):
+        w = np.ascontiguousarray(pack.weights)
+        b = np.ascontiguousarray(pack.bias)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        wq = np.ascontiguousarray(pack.weight_q, np.int32) if pack.weight_q is not None else None
+        bq = np.ascontiguousarray(pack.bias_q, np.int32) if pack.bias_q is not None else None
+        aq = np.ascontiguousarray(pack.act_q, np.int32) if pack.act_q is not None else None
+        nq = min(len(wq), len(bq)) if wq is not None else 0
+        rc = self.lib.yolo2cuda_net_load_weights(self.handle, vp(w), w.size, vp(b), b.size, vp(wq), vp(bq), nq,
+                                                 vp(aq), len(aq) if aq is not None else 0)
+        _capi.check(self.accel.ctx, rc)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.yolo2cuda_net_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- forward ---------------------------------------------------------------------------------
+    def forward(self, frames: np.ndarray, out: np.ndarray = None) -> np.ndarray:
+        """frames: float32 [B][c][h][w] on the HOST (pinned or not). Returns the region tensors
+        float32 [B][n][coords+1+classes][h][w] (layers[n-1].output per frame)."""
+        frames = np.ascontiguousarray(frames, np.float32)
+        B = frames.shape[0]
+        if out is None:
+            out = np.empty((B, self.region_outputs), np.float32)
+        rc = self.lib.yolo2cuda_net_forward_host(self.handle, frames.ctypes.data_as(C.c_void_p), B,
+                                                 out.ctypes.data_as(C.c_void_p))
+        _capi.check(self.accel.ctx, rc)
+        return self._shape_region(out, B)
+
+    def forward_ptr(self, frames_ptr: int, batch: int, out_ptr: int, device: bool):
+        """Raw-pointer form (torch tensors: .data_ptr()). device=True is asynchronous."""
+        fn = self.lib.yolo2cuda_net_forward_dev if device else self.lib.yolo2cuda_net_forward_host
+        _capi.check(self.accel.ctx, fn(self.handle, C.c_void_p(frames_ptr), batch, C.c_void_p(out_ptr)))
+
+    def _shape_region(self, flat, B):
+        l = self.net.layers[-1]
+        return flat.reshape(B, l.n, l.coords + 1 + l.classes, l.h, l.w)
+
+    def layer_output(self, layer: int, frame: int = 0) -> np.ndarray:
+        """ofm of `layer` for `frame` of the last forward, reference layout [out_c][out_h][ceil8 out_w]."""
+        l = self.net.layers[layer]
+        wa = (l.out_w + 7) & ~7
+        dst = np.zeros((l.out_c, l.out_h, wa), self.accel.dtype)
+        rc = self.lib.yolo2cuda_net_get_layer_output(self.handle, layer, frame, dst.ctypes.data_as(C.c_void_p), dst.size)
+        _capi.check(self.accel.ctx, rc)
+        return dst
+
+    @property
+    def region_q(self):
+        return int(self.lib.yolo2cuda_net_region_q(self.handle))
+
+    @property
+    def launches_per_forward(self):
+        return int(self.lib.yolo2cuda_net_launches_per_forward(self.handle))
+
+    def layer_times(self):
+        ms = np.zeros(len(self.net.layers), np.float32)
+        _capi.check(self.accel.ctx, self.lib.yolo2cuda_net_layer_times(self.handle, ms.ctypes.data_as(C.c_void_p), ms.size))
+        return ms
+
+    # -- detections (get_network_boxes + do_nms_sort, yolov2_main.cpp:311-320) --------------------
+    def detections(self, region: np.ndarray, im_w: int, im_h: int, thresh: float = 0.25, nms: float = 0.45):
+        return region_detections(self.net, region, im_w, im_h, thresh, nms)
+
+
+def region_detections(net: _cfg.Network, region: np.ndarray, im_w: int, im_h: int, thresh=0.25, nms=0.45):
+    """One frame's region tensor -> (boxes[k][4] x,y,w,h relative, probs[k][classes], objectness[k])."""
+    lib = _capi.load_library()
+    l = net.layers[-1]
+    total = l.w * l.h * l.n
+    region = np.ascontiguousarray(region, np.float32).reshape(-1)
+    boxes = np.zeros((total, 4), np.float32)
+    probs = np.zeros((total, l.classes), np.float32)
+    obj = np.zeros(total, np.float32)
+    anchors = np.asarray(l.anchors, np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    k = lib.yolo2cuda_region_detections(vp(region), l.w, l.h, l.n, l.classes, vp(anchors), im_w, im_h, net.w, net.h,
+                                        C.c_float(thresh), C.c_float(nms), vp(boxes), vp(probs), vp(obj))
+    if k < 0:
+        raise _capi.Yolo2CudaError(k, "yolo2cuda_region_detections failed")
+    return boxes[:k], probs[:k], obj[:k]
+
+
+def yolov2_cuda_ps(net: _cfg.Network, input: np.ndarray, pack: WeightsPack, device: int = 0) -> np.ndarray:
+    """Single-frame mirror of yolov2_hls_ps(net, input, precision): returns layers[n-1].output."""
+    y = Yolo2Net(net, pack, device=device, max_batch=1)
+    try:
+        return y.forward(np.asarray(input, np.float32).reshape(1, net.c, net.h, net.w))[0]
+    finally:
+        y.close()
