@@ -49,7 +49,8 @@ def test_conv_int16_saturation_and_extremes(amp, q, accel16, oracle):
     want = oracle_conv(oracle, a, x, wr, b, q)
     got = accel_call(accel16, a, x, wr, b, q)
     assert np.array_equal(valid(got, 20), valid(want, 20))
-    assert (np.abs(valid(want, 20).astype(int)) >= 32767).mean() > 0.05 or q[2] == 0
+    if q[2] == 12:
+        assert (np.abs(valid(want, 20).astype(int)) >= 32767).mean() > 0.05      # the case really saturates
 
 
 def test_conv_pad_columns_untouched(accel16):

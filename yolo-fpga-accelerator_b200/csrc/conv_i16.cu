@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
     const int zero_slot = xrows - 1;
     const int x_stage_px = p.GS * xrows * p.PW;  // uint2 elements
     const int w_stage_px = p.GS * K2 * kCM;      // uint2 elements
-    const int stage_px = x_stage_px + w_stage_px;
+    const int stage_px = (x_stage_px + w_stage_px + 1) & ~1;  // weights first: keeps their 16-byte cp.async aligned
     uint2 *sm = reinterpret_cast<uint2 *>(smem_raw);
 
     const int tid = threadIdx.x;
@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
     auto load_stage = [&](int st, int buf) {
         const int g0 = st * p.GS;
         const int ng = min(p.GS, p.G - g0);
-        uint2 *xs = sm + buf * stage_px;
-        uint2 *wsm = xs + x_stage_px;
+        uint2 *wsm = sm + buf * stage_px;
+        uint2 *xs = wsm + w_stage_px;
         const int nrows = p.RB + KS - 1;
         const int per_group = nrows * p.W;
         for (int idx = tid; idx < ng * per_group; idx += kThreads) {
@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
             cp_async_wait<0>();
         }
         __syncthreads();
-        const uint2 *xs = sm + (st & 1) * stage_px;
-        const uint2 *wsm = xs + x_stage_px + wm * kTMC;
+        const uint2 *wsm = sm + (st & 1) * stage_px + wm * kTMC;
+        const uint2 *xs = sm + (st & 1) * stage_px + w_stage_px;
         const int ng = min(p.GS, p.G - st * p.GS);
         for (int gg = 0; gg < ng; ++gg) {
             const uint2 *xg = xs + gg * xrows * p.PW;
@@ -338,7 +338,7 @@ size_t conv_fast_plan(ConvFastParams &p, int ksize, int elem_bytes)
     if (gs > 8) gs = 8;
     if (gs > p.G) gs = p.G;
     p.GS = gs;
-    size_t smem = 2 * per_group * gs;
+    size_t smem = 2 * per_group * gs + 64;
     if (smem > 200 * 1024) return 0;
     return smem;
 }
@@ -362,7 +362,7 @@ static int launch_i16_variant(const ConvFastParams &p, size_t smem, cudaStream_t
 int launch_conv_i16_fast(const ConvFastParams &p, int ksize, cudaStream_t st, const char **variant)
 {
     const int xrows = p.RB + ksize - 1 + 1;
-    const size_t smem = 2 * (size_t)p.GS * ((size_t)xrows * p.PW + (size_t)ksize * ksize * kCM) * 8;
+    const size_t smem = 2 * (((size_t)p.GS * ((size_t)xrows * p.PW + (size_t)ksize * ksize * kCM) + 1) & ~(size_t)1) * 8;
     const int tp = p.TP;
     if (tp == 13 && ksize == 3) { if (variant) *variant = "conv_i16_c4<13,3>"; return launch_i16_variant<13, 3>(p, smem, st); }
     if (tp == 13 && ksize == 1) { if (variant) *variant = "conv_i16_c4<13,1>"; return launch_i16_variant<13, 1>(p, smem, st); }
