@@ -12,14 +12,18 @@ pytestmark = pytest.mark.gpu
 
 CONV_CASES = [
     # c, n, size, stride, w, h, leaky, (Qw, Qa_in, Qa_out, Qb), expected kernel prefix
-    (3, 32, 3, 1, 26, 26, 1, (14, 10, 10, 10), "conv_i16_c4<13,3>"),
-    (64, 32, 3, 1, 13, 13, 1, (14, 10, 10, 10), "conv_i16_c4<13,3>"),
-    (32, 64, 3, 1, 52, 39, 1, (14, 10, 10, 10), "conv_i16_c4<13,3>"),
-    (128, 64, 1, 1, 26, 26, 1, (14, 10, 10, 10), "conv_i16_c4<13,1>"),
-    (16, 425, 1, 1, 13, 13, 0, (12, 12, 7, 8), "conv_i16_c4<13,1>"),
-    (20, 40, 3, 1, 19, 19, 1, (13, 9, 12, 11), "conv_i16_c4<7,3>"),
+    (3, 32, 3, 1, 26, 26, 1, (14, 10, 10, 10), "conv_i16_c4<13,3,scaled"),
+    (64, 32, 3, 1, 13, 13, 1, (14, 10, 10, 10), "conv_i16_c4<13,3,scaled"),
+    (32, 64, 3, 1, 52, 39, 1, (14, 10, 10, 10), "conv_i16_c4<13,3,scaled"),
+    (128, 64, 1, 1, 26, 26, 1, (14, 10, 10, 10), "conv_i16_c4<13,1,scaled"),
+    (16, 425, 1, 1, 13, 13, 0, (12, 12, 7, 8), "conv_i16_c4<13,1,scaled"),
+    (20, 40, 3, 1, 19, 19, 1, (13, 9, 12, 11), "conv_i16_c4<7,3,scaled"),
     (7, 9, 3, 1, 33, 5, 0, (14, 10, 10, 10), "conv_i16_c4"),
-    (40, 24, 1, 1, 19, 7, 1, (15, 10, 10, 2), "conv_i16_c4<7,1>"),
+    (40, 24, 1, 1, 19, 7, 1, (15, 10, 10, 2), "conv_i16_c4<7,1,scaled"),
+    (24, 32, 3, 1, 26, 13, 1, (15, 12, 2, 10), "conv_i16_c4<13,3,unscaled"),   # shift_out = 25 > 22
+    (24, 20, 1, 1, 14, 9, 0, (15, 15, 0, 3), "conv_i16_c4<7,1,unscaled"),      # shift_out = 30
+    (16, 16, 3, 1, 13, 13, 1, (15, 15, 8, 0), "conv_i16_c4<13,3,scaled"),      # shift_out = 22 (largest scaled)
+    (16, 16, 3, 1, 13, 13, 1, (4, 10, 6, 12), "conv_i16_c4<13,3,scaled"),      # shift_out = 8 (smallest), bias shift left
     (32, 70, 3, 2, 27, 19, 0, (14, 10, 9, 12), "conv_i16_generic"),      # stride 2
     (8, 8, 3, 1, 9, 9, 1, (3, 3, 10, 12), "conv_i16_generic"),           # negative shift_out
     (8, 16, 3, 1, 13, 13, 1, (10, 5, 10, 10), "conv_i16_generic"),       # shift_out = 5 < 8

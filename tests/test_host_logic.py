@@ -1,0 +1,129 @@
+"""Host-side logic and the C-ABI surface, without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from yolo2_b200 import _capi, cfg as ycfg, weights as yw
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _capi.load_library()
+    header = open(os.path.join(ROOT, "include", "yolo2cuda.h")).read()
+    declared = set(re.findall(r"\b(yolo2cuda_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_no_gpu_means_init_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _capi.load_library()
+    ctx = C.c_void_p()
+    assert lib.yolo2cuda_create(C.byref(ctx), 0, 16) == _capi.INIT_ERROR
+    from yolo2_b200.accel import Accelerator
+    with pytest.raises(_capi.Yolo2CudaError):
+        Accelerator(0, "int16")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "yolo-fpga-accelerator_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(d, f), errors="ignore").read()
+                for pat in ("import oracle", "from oracle", "oracle/", "liboracle", "orc_", "_ref/", "libref"):
+                    assert pat not in txt, f"{f} references the checker ({pat})"
+
+
+def test_cfg_matches_reference_model_tables():
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 80))
+    assert len(net.layers) == 32
+    counts = net.weight_counts()
+    # hls/models/yolov2/model_config.cpp:4-10
+    assert [c[0] for c in counts] == [864, 18432, 73728, 8192, 73728, 294912, 32768, 294912, 1179648, 131072, 1179648,
+                                      131072, 1179648, 4718592, 524288, 4718592, 524288, 4718592, 9437184, 9437184,
+                                      32768, 11796480, 435200]
+    assert [c[1] for c in counts] == [32, 64, 128, 64, 128, 256, 128, 256, 512, 256, 512, 256, 512, 1024, 512, 1024, 512,
+                                      1024, 1024, 1024, 64, 1024, 425]
+    assert sum(c[0] for c in counts) == 50941792 and sum(c[1] for c in counts) == 10761
+    l = net.layers
+    assert (l[25].type, l[25].inputs) == (ycfg.ROUTE, [16]) and (l[28].type, l[28].inputs) == (ycfg.ROUTE, [27, 24])
+    assert (l[27].out_c, l[27].out_h, l[27].out_w) == (256, 13, 13) and l[29].c == 1280
+    assert (l[31].n, l[31].classes, l[31].w) == (5, 80, 13)
+    big = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(608, 608, 80))
+    assert [x.out_w for x in big.layers if x.type == ycfg.MAXPOOL] == [304, 152, 76, 38, 19]
+
+
+def test_cfg_rejects_sections_outside_the_path():
+    with pytest.raises(ValueError):
+        ycfg.parse_network_cfg("[net]\nwidth=32\nheight=32\nchannels=3\n[upsample]\nstride=2\n")
+    with pytest.raises(ValueError):
+        ycfg.parse_network_cfg("[convolutional]\nfilters=3\n\n")
+
+
+def test_weight_reorg_formula_and_oracle_agree(oracle):
+    rng = np.random.default_rng(0)
+    for ifm, ofm, k in [(3, 32, 3), (64, 70, 3), (17, 425, 1), (5, 5, 2)]:
+        w = rng.integers(-999, 999, (ofm, ifm, k * k)).astype(np.int16)
+        tm, tn = min(ofm, 32), min(ifm, 4)
+        a = yw.weight_reorg(w, ifm, ofm, k, tm, tn)
+        assert np.array_equal(a, oracle.weight_reorg(w, ifm, ofm, k, tm, tn))
+        # SURVEY.md appendix A address formula
+        for _ in range(50):
+            m, c, t = int(rng.integers(ofm)), int(rng.integers(ifm)), int(rng.integers(k * k))
+            m0, n0 = (m // tm) * tm, (c // tn) * tn
+            tmm, tnn = min(tm, ofm - m0), min(tn, ifm - n0)
+            off = m0 * ifm * k * k + tmm * n0 * k * k + (t * tmm + (m - m0)) * tnn + (c - n0)
+            assert a[off] == w[m, c, t]
+
+
+def test_weight_files_roundtrip_with_odd_length_padding(tmp_path):
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 80, channel_div=16))
+    pack = yw.synth_pack(net, "int16", seed=3, table="stress")
+    yw.save_reference_files(pack, net, str(tmp_path))
+    # the 425-entry bias layer is odd: one pad element follows it in the file (yolo2_model.cpp:216-223)
+    nb = os.path.getsize(tmp_path / "bias_int16.bin") // 2
+    assert nb == pack.bias.size + sum(c[1] & 1 for c in net.weight_counts())
+    back = yw.load_reference_files(net, "int16", str(tmp_path))
+    assert np.array_equal(back.weights, pack.weights) and np.array_equal(back.bias, pack.bias)
+    assert np.array_equal(back.act_q, pack.act_q)
+    (tmp_path / "weights_reorg_int16.bin").write_bytes(b"\0" * 10)
+    with pytest.raises(RuntimeError, match="weights file too small"):
+        yw.load_reference_files(net, "int16", str(tmp_path))
+
+
+def test_quantize_input_rounding(oracle):
+    x = np.array([0.0, 0.5, -0.5, 1.5 / 1024, 2.5 / 1024, -2.5 / 1024, 40.0, -40.0, 0.99999], np.float32)
+    q = oracle.quantize_input(x, 10)
+    assert q.tolist() == [0, 512, -512, 2, 3, -3, 32767, -32768, 1024]   # half away from zero, saturating
+
+
+def test_round_shift_semantics(oracle):
+    assert oracle.round_shift(5, 1) == 3 and oracle.round_shift(-5, 1) == -2        # half up toward +inf
+    assert oracle.round_shift(-1, 4) == 0 and oracle.round_shift(-9, 4) == -1
+    assert oracle.round_shift(3, -2) == 12 and oracle.round_shift(7, 0) == 7
+    assert oracle.round_shift(1 << 40, 35) == oracle.round_shift(1 << 40, 30)       # |shift| clamped to 30
+
+
+def test_host_detections_match_oracle(oracle):
+    from yolo2_b200.model import region_detections
+    rng = np.random.default_rng(5)
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 80))
+    l = net.layers[-1]
+    region = oracle.region_forward(rng.normal(0, 2.5, (425, 13, 13)).astype(np.float32), 13, 13, 5, 80)
+    for im_w, im_h, thresh in [(768, 576, 0.2), (300, 500, 0.05)]:
+        b, p, o = region_detections(net, region, im_w, im_h, thresh, 0.45)
+        wb, wp, wo = oracle.region_boxes_nms(region, 13, 13, 5, 80, l.anchors, im_w, im_h, 416, 416, thresh, 0.45)
+        live = wo > 0
+        key = lambda bb, pp, oo: sorted((tuple(x.tolist()), float(z), tuple(np.nonzero(q)[0].tolist()), tuple(q[q > 0].tolist()))
+                                        for x, q, z in zip(bb, pp, oo))
+        assert len(b) == live.sum() > 10
+        assert key(b, p, o) == key(wb[live], wp[live], wo[live])

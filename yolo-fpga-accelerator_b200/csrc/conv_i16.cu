@@ -9,10 +9,15 @@
 //
 // Because the accumulator is rounded and saturated after EVERY 4-MAC step, the work per step is
 // fixed-function integer ALU work; a big-K tensor-core GEMM is not bit-exact.
-// The fast kernel spends exactly 7 SASS instructions per step and output:
-//   4x IDP.2A  (int16 activations x weight bytes: P = 256*sum(x*w_hi) + sum(x*w_lo), no overflow)
-//   2x SHF     ((Plo+half)>>8 folded into the hi chain's addend, then >>(so-8))
-//   1x VIADDMNMX.RELU  (accumulator kept as acc+32768 in [0,65535]: add+min+relu = saturating add)
+// The fast kernel spends exactly 7 SASS instructions per step and output.  IDP.2A and VIADDMNMX
+// issue at half rate on B200 (profiles/microbench), LEA/LOP3/VIMNMX/SHF at full rate, so the
+// preferred "scaled" form keeps only the four IDP.2A on the half-rate pipe:
+//   4x IDP.2A       int16 activations x weight bytes: P = 256*sum(x*w_hi) + sum(x*w_lo), no overflow
+//   1x LEA.HI.SX32  U + ((Plo+half)>>8) as the hi chain's addend; U = (acc+32768) << (so-8) is the state
+//   1x LOP3         drop the fraction bits (the per-step floor)
+//   1x VIMNMX.RELU  clamp to [0, 65535<<(so-8)] = the 16-bit saturation
+// (valid for 8 <= so <= 22).  For 23 <= so <= 30 the unscaled form is used:
+//   4x IDP.2A, 2x SHF, 1x VIADDMNMX.RELU (accumulator kept as acc+32768 in [0,65535]).
 #include "common.cuh"
 
 namespace y2 {
@@ -69,7 +74,7 @@ constexpr int kThreads = 32 * kWM * kWS;
 
 // One CTA: a band of RB image rows (flattened over frames) x 16 output channels.
 // One thread: one row segment of TP pixels x 4 output channels = 4*TP saturating accumulators.
-template <int TP, int KS>
+template <int TP, int KS, bool SCALED>
 __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFastParams p)
 {
     constexpr int K2 = KS * KS;
@@ -139,7 +144,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
         for (int idx = tid; idx < nw16; idx += kThreads) cp_async16(wsm + idx * 2, wg + idx * 2);
     };
 
-    // accumulators hold acc+32768 in [0,65535]
+    // accumulators hold acc+32768 in [0,65535], pre-shifted left by k2 in the SCALED form
+    const int half = 1 << (p.so - 1);
+    const int k2 = p.so - 8;
+    const int nmask = ~((1 << k2) - 1);
+    const int ubound = 65535 << (SCALED ? k2 : 0);
     int acc[kTMC][TP];
     {
         const int16_t *bias = static_cast<const int16_t *>(p.bias);
@@ -148,15 +157,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
             int m = mb * kCM + wm * kTMC + c;
             long long b = (m < p.OFM) ? (long long)bias[m] : 0;
             long long base = round_shift64(b, p.sb);
-            // |rs(P,so)| < 2^25 on this path, so clamping base to +-2^26 cannot change clamp16(base+r)
-            if (base > (1 << 26)) base = (1 << 26);
-            if (base < -(1 << 26)) base = -(1 << 26);
+            // |rs(P,so)| <= rb on this path, so clamping base+32768 to [-rb, 65535+rb] cannot change
+            // clamp(base+32768+r, 0, 65535); it keeps the (scaled) state inside int32
+            const long long rb = (SCALED ? ((1LL << 25) >> k2) : (1LL << 26)) + 2;
+            long long boff = base + 32768;
+            if (boff > 65535 + rb) boff = 65535 + rb;
+            if (boff < -rb) boff = -rb;
+            const int init = SCALED ? (int)(boff * (1LL << k2)) : (int)boff;
 #pragma unroll
-            for (int q = 0; q < TP; ++q) acc[c][q] = (int)base + 32768;
+            for (int q = 0; q < TP; ++q) acc[c][q] = init;
         }
     }
-    const int half = 1 << (p.so - 1);
-    const int k2 = p.so - 8;
 
     const int nstages = (p.G + p.GS - 1) / p.GS;
     load_stage(0, 0);
@@ -198,9 +209,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
                             const uint2 x = xv[q + j];
                             int plo = dp2a_lo_su((int)x.x, wv[c].x, half);
                             plo = dp2a_hi_su((int)x.y, wv[c].x, plo);
-                            int phi = dp2a_lo_ss((int)x.x, (int)wv[c].y, plo >> 8);
-                            phi = dp2a_hi_ss((int)x.y, (int)wv[c].y, phi);
-                            acc[c][q] = __viaddmin_s32_relu(acc[c][q], phi >> k2, 65535);
+                            if (SCALED) {
+                                int phi = dp2a_lo_ss((int)x.x, (int)wv[c].y, acc[c][q] + (plo >> 8));
+                                phi = dp2a_hi_ss((int)x.y, (int)wv[c].y, phi);
+                                acc[c][q] = __vimin_s32_relu(phi & nmask, ubound);
+                            } else {
+                                int phi = dp2a_lo_ss((int)x.x, (int)wv[c].y, plo >> 8);
+                                phi = dp2a_hi_ss((int)x.y, (int)wv[c].y, phi);
+                                acc[c][q] = __viaddmin_s32_relu(acc[c][q], phi >> k2, 65535);
+                            }
                         }
                 }
             }
@@ -218,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
         int v[kTMC];
 #pragma unroll
         for (int c = 0; c < kTMC; ++c) {
-            int a = acc[c][q] - 32768;
+            int a = (SCALED ? (acc[c][q] >> k2) : acc[c][q]) - 32768;
             if (p.leaky && a < 0) a = a / 10;  // C division, truncates toward zero
             v[c] = a & 0xffff;
         }
@@ -344,18 +361,18 @@ size_t conv_fast_plan(ConvFastParams &p, int ksize, int elem_bytes)
 }
 
 
-template <int TP, int KS>
+template <int TP, int KS, bool SCALED>
 static int launch_i16_variant(const ConvFastParams &p, size_t smem, cudaStream_t st)
 {
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(conv_i16_c4_kernel<TP, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_i16_c4_kernel<TP, KS, SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         configured[dev] = true;
     }
     dim3 grid(ceil_div(p.B * p.H, p.RB), ceil_div(p.OFM, kCM));
-    conv_i16_c4_kernel<TP, KS><<<grid, kThreads, smem, st>>>(p);
+    conv_i16_c4_kernel<TP, KS, SCALED><<<grid, kThreads, smem, st>>>(p);
     return 1;
 }
 
@@ -364,10 +381,17 @@ int launch_conv_i16_fast(const ConvFastParams &p, int ksize, cudaStream_t st, co
     const int xrows = p.RB + ksize - 1 + 1;
     const size_t smem = 2 * (((size_t)p.GS * ((size_t)xrows * p.PW + (size_t)ksize * ksize * kCM) + 1) & ~(size_t)1) * 8;
     const int tp = p.TP;
-    if (tp == 13 && ksize == 3) { if (variant) *variant = "conv_i16_c4<13,3>"; return launch_i16_variant<13, 3>(p, smem, st); }
-    if (tp == 13 && ksize == 1) { if (variant) *variant = "conv_i16_c4<13,1>"; return launch_i16_variant<13, 1>(p, smem, st); }
-    if (tp == 7 && ksize == 3) { if (variant) *variant = "conv_i16_c4<7,3>"; return launch_i16_variant<7, 3>(p, smem, st); }
-    if (tp == 7 && ksize == 1) { if (variant) *variant = "conv_i16_c4<7,1>"; return launch_i16_variant<7, 1>(p, smem, st); }
+    const bool scaled = p.so <= 22;
+#define Y2_VARIANT(TPV, KSV)                                                                                  \
+    if (tp == TPV && ksize == KSV) {                                                                           \
+        if (variant) *variant = scaled ? "conv_i16_c4<" #TPV "," #KSV ",scaled>" : "conv_i16_c4<" #TPV "," #KSV ",unscaled>"; \
+        return scaled ? launch_i16_variant<TPV, KSV, true>(p, smem, st) : launch_i16_variant<TPV, KSV, false>(p, smem, st); \
+    }
+    Y2_VARIANT(13, 3)
+    Y2_VARIANT(13, 1)
+    Y2_VARIANT(7, 3)
+    Y2_VARIANT(7, 1)
+#undef Y2_VARIANT
     return -1;
 }
 

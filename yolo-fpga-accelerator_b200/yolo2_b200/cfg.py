@@ -168,7 +168,7 @@ def to_desc_array(net: Network):
 # bench.py and smoke() do not need /root/reference at run time.  VOC differs only in the head.
 def yolov2_cfg_text(width=416, height=416, classes=80, anchors=None, channel_div=1):
     """channel_div > 1 thins every hidden layer (filters // channel_div, at least 4): the same 32-section
-    topology and spatial sizes at a fraction of the work, for oracle-speed tests."""
+    topology and spatial sizes at a fraction of the work, for quick parity tests."""
     anchors = anchors or ("0.57273, 0.677385, 1.87446, 2.06253, 3.33843, 5.47434, 7.88282, 3.52778, 9.77052, 9.16828"
                           if classes == 80 else
                           "1.3221, 1.73145, 3.19275, 4.00944, 5.05587, 8.09892, 9.47112, 4.84053, 11.2364, 10.0071")
