@@ -192,3 +192,130 @@ def test_batch_linearity_and_idempotence(oracle):
         y.close()
     want, _ = oracle.net_forward(net, frames[7], pack)
     assert np.array_equal(r1[7].view(np.uint32), want.view(np.uint32))
+
+
+# ---- golden fixtures (outputs of the real reference) through the CUDA path -------------------------
+
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layer_cases.npz"))
+
+
+def _gargs(arr):
+    from oracle.gen_golden import ARG_KEYS
+    return dict(zip(ARG_KEYS, [int(v) for v in arr]))
+
+
+@pytest.mark.parametrize("i", range(9))
+def test_cuda_conv_int16_vs_reference_golden(i, accel16):
+    g = _golden()
+    a = _gargs(g[f"ci16_{i}_args"])
+    got = accel_call(accel16, a, g[f"ci16_{i}_x"], g[f"ci16_{i}_w"], g[f"ci16_{i}_b"], [int(v) for v in g[f"ci16_{i}_q"]])
+    ow = a["Output_w"]
+    assert np.array_equal(valid(got, ow), valid(g[f"ci16_{i}_out"], ow))
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_cuda_conv_fp32_vs_reference_golden(i, accel32):
+    g = _golden()
+    a = _gargs(g[f"cf32_{i}_args"])
+    got = accel_call(accel32, a, g[f"cf32_{i}_x"], g[f"cf32_{i}_w"], g[f"cf32_{i}_b"])
+    ow = a["Output_w"]
+    want = valid(g[f"cf32_{i}_out"], ow)
+    assert np.abs(valid(got, ow) - want).max() <= 1e-4 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_cuda_maxpool_vs_reference_golden(i, accel16, accel32):
+    g = _golden()
+    a = _gargs(g[f"pool_{i}_args"])
+    ow = a["Output_w"]
+    assert np.array_equal(valid(accel_call(accel16, a, g[f"pool_{i}_x"], None, None), ow), valid(g[f"pool_{i}_out"], ow))
+    assert np.array_equal(valid(accel_call(accel32, a, g[f"poolf_{i}_x"], None, None), ow), valid(g[f"poolf_{i}_out"], ow))
+
+
+@pytest.mark.parametrize("tag,table,seed", [("default", "default", 1), ("stress", "stress", 2)])
+def test_cuda_full_coco416_vs_reference_golden(tag, table, seed):
+    """--backend cuda vs the UNMODIFIED yolov2_hls_ps: region tensor of layers[31].output, bit for bit."""
+    import hashlib
+    import os
+    full = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "yolov2_coco416_full.npz"))
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 80))
+    pack = yw.synth_pack(net, "int16", seed=seed, table=table)
+    frame = yw.synth_frames(net, 1, seed=1000)
+    if hashlib.sha256(pack.weights.tobytes()).digest() != full[f"{tag}_weights_sha"].tobytes():
+        pytest.skip("numpy RNG stream differs from the one the golden was generated with")
+    from yolo2_b200.model import yolov2_cuda_ps
+    region = yolov2_cuda_ps(net, frame[0], pack)
+    assert np.array_equal(region.reshape(-1).view(np.uint32), full[f"{tag}_region"].view(np.uint32))
+
+
+# ---- LayerType 2 and the driver-side operators on device memory -------------------------------------
+
+@pytest.mark.parametrize("ch,ow,oh,TM", [(4, 13, 13, 4), (8, 26, 20, 4), (4, 5, 5, 2), (6, 7, 9, 4)])
+def test_reorg_layertype2(ch, ow, oh, TM, accel16, oracle):
+    rng = np.random.default_rng(ch * ow)
+    iw, ih = 2 * ow, 2 * oh
+    mLoops = -(-ch // TM)
+    a = dict(IFM_num=ch, OFM_num=ch, Ksize=2, Kstride=2, Input_w=iw, Input_h=ih, Output_w=ow, Output_h=oh, Padding=0,
+             IsNL=0, IsBN=0, TM=TM, TN=0, TR=min(13, oh), TC=min(13, ow), OFM_num_bound=(mLoops + 2) * TM,
+             mLoopsxTM=mLoops * TM, mLoops_a1xTM=(mLoops + 1) * TM, LayerType=2)
+    x = np.zeros((ch, ih, align8(iw)), np.int16)
+    x[:, :, :iw] = rng.integers(-30000, 30000, (ch, ih, iw))
+    want = oracle.reorg_hls(x, ch, TM, iw, ih, ow, oh)
+    got = accel_call(accel16, a, x, None, None)
+    # tile channels beyond the four phases are never written by the reference: compare written ones
+    written = [m + q for m in range(0, ch, TM) for q in range(min(TM, ch - m, 4))]
+    assert np.array_equal(valid(got, ow)[written], valid(want, ow)[written])
+
+
+def test_driver_side_operators_on_device(accel16, oracle):
+    import ctypes as C
+    import torch
+    lib, ctx = accel16.lib, accel16.ctx
+    rng = np.random.default_rng(0)
+    # input quantiser
+    x = (rng.random(3 * 32 * 32, dtype=np.float32) * 80 - 40).astype(np.float32)
+    x[:6] = [0.5, -0.5, 1.5 / 1024, 2.5 / 1024, -2.5 / 1024, 0.0]
+    dx = torch.from_numpy(x).cuda()
+    dq = torch.empty(x.size, dtype=torch.int16, device="cuda")
+    assert lib.yolo2cuda_quantize_input_dev(ctx, C.c_void_p(dx.data_ptr()), C.c_void_p(dq.data_ptr()), x.size, 10) == 0
+    accel16.synchronize()
+    assert np.array_equal(dq.cpu().numpy(), oracle.quantize_input(x, 10))
+    # flat-memory reorg + Q-align shift (26x26x64 is the reference's own case; 38x38x16 a 608-net one)
+    for c, h, w, shift in [(64, 26, 26, 0), (64, 26, 26, 3), (16, 38, 38, 1)]:
+        t = np.zeros((c, h, align8(w)), np.int16)
+        t[:, :, :w] = rng.integers(-32768, 32768, (c, h, w))
+        want = oracle.reorg_driver(t, c, h, w, shift)
+        din = torch.from_numpy(t).cuda()
+        dout = torch.full(want.shape, 99, dtype=torch.int16, device="cuda")
+        assert lib.yolo2cuda_reorg_dev(ctx, C.c_void_p(din.data_ptr()), C.c_void_p(dout.data_ptr()), c, h, w, shift) == 0
+        accel16.synchronize()
+        assert np.array_equal(dout.cpu().numpy(), want)        # including the zeroed pad columns (yolo2_model.cpp:375)
+    # region head
+    for classes, n, w in [(80, 5, 13), (20, 5, 19)]:
+        ch = n * (5 + classes)
+        t = np.zeros((ch, w, align8(w)), np.int16)
+        t[:, :, :w] = rng.integers(-6000, 6000, (ch, w, w))
+        want = oracle.region_from_ofm(t, w, w, n, classes, 4, 1, 0, q=9)
+        din = torch.from_numpy(t).cuda()
+        dout = torch.empty(want.size, dtype=torch.float32, device="cuda")
+        assert lib.yolo2cuda_region_dev(ctx, C.c_void_p(din.data_ptr()), C.c_void_p(dout.data_ptr()), w, w, n, classes, 4, 1, 0, 9) == 0
+        accel16.synchronize()
+        assert np.array_equal(dout.cpu().numpy().view(np.uint32), want.reshape(-1).view(np.uint32))
+    assert lib.yolo2cuda_reorg_dev(ctx, C.c_void_p(din.data_ptr()), C.c_void_p(dout.data_ptr()), 3, 5, 5, 0) == -1
+
+
+def test_layer_dev_entry_matches_host_entry(accel16, oracle):
+    """yolo2cuda_layer_dev on torch device tensors == the host entry == the oracle."""
+    import torch
+    a, x, wr, b, _ = make_conv_case(5, 32, 48, 3, 1, 26, 26, 1)
+    q = (14, 10, 10, 10)
+    want = oracle_conv(oracle, a, x, wr, b, q)
+    dx, dw, db = (torch.from_numpy(t).cuda() for t in (x, wr, b))
+    dout = torch.zeros(want.shape, dtype=torch.int16, device="cuda")
+    accel16.YOLO2_FPGA_dev(dx.data_ptr(), dout.data_ptr(), dw.data_ptr(), db.data_ptr(), *[a[k] for k in (
+        "IFM_num", "OFM_num", "Ksize", "Kstride", "Input_w", "Input_h", "Output_w", "Output_h", "Padding", "IsNL",
+        "IsBN", "TM", "TN", "TR", "TC", "OFM_num_bound", "mLoopsxTM", "mLoops_a1xTM", "LayerType")], *q)
+    accel16.synchronize()
+    assert np.array_equal(valid(dout.cpu().numpy(), 26), valid(want, 26))
