@@ -6,7 +6,7 @@
 
 A "step" is one pass of the whole datapath (quantise -> 23 conv / 5 pool / reorg / route -> region)
 over one batch of synthetic 416x416 frames.  Weak scaling: every GPU processes --frames-per-gpu
-frames per step (default 128, i.e. BASELINE configs[4]'s 1024-frame stream at 8 GPUs); ranks are
+frames per step (default 512: BASELINE configs[4]'s frame stream, 4096 frames per step at 8 GPUs); ranks are
 independent (frames shard with no data-path collective) and NCCL only gathers the region tensors.
 Prints ONE JSON line on rank 0.
 """
@@ -143,8 +143,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-gpu", type=int, default=128)
-    ap.add_argument("--chunk", type=int, default=64, help="frames per device pass (arena size)")
+    ap.add_argument("--frames-per-gpu", type=int, default=512)
+    ap.add_argument("--chunk", type=int, default=256, help="frames per device pass (arena size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes for the cpu_baseline leg (default min(cores,32))")
@@ -281,8 +281,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int16", "data": "synthetic",
-                "config": {"workload": f"YOLOv2 COCO 416x416 INT16, {B} frames/GPU/step (BASELINE configs[4] frame stream; "
-                                       f"1024 frames at 8 GPUs), device passes of {y.max_batch} frames",
+                "config": {"workload": f"YOLOv2 COCO 416x416 INT16 frame stream (BASELINE configs[4]), {B} frames/GPU/step, "
+                                       f"device passes of {y.max_batch} frames",
                            "global_batch": world * B, "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
                            "l2": f"inputs {B * frame_bytes >> 20} MiB per step > 126 MB L2 (no flush needed)",
                            "weights": "seeded synthetic int16, Qw=14 Qb=10 Qa=10"},

@@ -62,9 +62,22 @@ __global__ void __launch_bounds__(kThreads, 2) conv_f32_c4_kernel(const ConvFast
     }
 
     for (int i = tid; i < 2 * stage_px; i += kThreads) sm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int2 *tbl = reinterpret_cast<int2 *>(sm + 2 * stage_px);   // per-CTA copy table, see conv_i16.cu
+    const int n_tbl = (p.RB + KS - 1) * p.W;
+    for (int idx = tid; idx < n_tbl; idx += kThreads) {
+        int s = idx / p.W, x = idx - s * p.W;
+        int Rr = R0 - PAD + s;
+        int2 e = make_int2(-1, 0);
+        if (Rr >= 0 && Rr < rows_total) {
+            int ff = Rr / p.H, yy = Rr - ff * p.H;
+            e.x = (int)(ff * (p.in_frame_stride >> 2)) + yy * p.W + x;
+            e.y = s * p.PW + PAD + x;
+        }
+        tbl[idx] = e;
+    }
     __syncthreads();
 
-    const float *in = static_cast<const float *>(p.in);
+    const float4 *in_px = static_cast<const float4 *>(p.in);
     const float4 *wsrc = static_cast<const float4 *>(p.w) + (size_t)mb * p.G * K2 * kCM;
 
     auto load_stage = [&](int st, int buf) {
@@ -72,19 +85,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_f32_c4_kernel(const ConvFast
         const int ng = min(p.GS, p.G - g0);
         float4 *xs = sm + buf * stage_px;
         float4 *wsm = xs + x_stage_px;
-        const int nrows = p.RB + KS - 1;
-        const int per_group = nrows * p.W;
-        for (int idx = tid; idx < ng * per_group; idx += kThreads) {
-            int gg = idx / per_group;
-            int rem = idx - gg * per_group;
-            int s = rem / p.W;
-            int x = rem - s * p.W;
-            int Rr = R0 - PAD + s;
-            if (Rr >= 0 && Rr < rows_total) {
-                int ff = Rr / p.H, yy = Rr - ff * p.H;
-                const float *src = in + (size_t)ff * p.in_frame_stride + (((size_t)(g0 + gg) * p.H + yy) * p.W + x) * 4;
-                cp_async16(xs + (gg * xrows + s) * p.PW + PAD + x, src);
-            }
+        const int plane = p.H * p.W;
+        for (int idx = tid; idx < n_tbl; idx += kThreads) {
+            const int2 e = tbl[idx];
+            if (e.x < 0) continue;
+            const float4 *src = in_px + e.x + (size_t)g0 * plane;
+            float4 *dst = xs + e.y;
+            for (int gg = 0; gg < ng; ++gg) cp_async16(dst + gg * xrows * p.PW, src + (size_t)gg * plane);
         }
         const float4 *wg = wsrc + (size_t)g0 * K2 * kCM;
         for (int idx = tid; idx < ng * K2 * kCM; idx += kThreads) cp_async16(wsm + idx, wg + idx);
@@ -239,7 +246,8 @@ int launch_f32_variant(const ConvFastParams &p, size_t smem, cudaStream_t st)
 int launch_conv_f32_fast(const ConvFastParams &p, int ksize, cudaStream_t st, const char **variant)
 {
     const int xrows = p.RB + ksize - 1 + 1;
-    const size_t smem = 2 * (size_t)p.GS * ((size_t)xrows * p.PW + (size_t)ksize * ksize * kCM) * 16;
+    const size_t smem = 2 * (size_t)p.GS * ((size_t)xrows * p.PW + (size_t)ksize * ksize * kCM) * 16 +
+                        (size_t)(p.RB + ksize - 1) * p.W * 8;  // + the copy table
     if (p.TP != 7) return -1;
     if (ksize == 3) { if (variant) *variant = "conv_f32_c4<7,3>"; return launch_f32_variant<7, 3>(p, smem, st); }
     if (ksize == 1) { if (variant) *variant = "conv_f32_c4<7,1>"; return launch_f32_variant<7, 1>(p, smem, st); }

@@ -114,9 +114,24 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
 
     // zero both stage buffers once: halo columns, out-of-image rows and the zero row stay zero
     for (int i = tid; i < 2 * stage_px; i += kThreads) sm[i] = make_uint2(0u, 0u);
+    // per-CTA copy table: (source pixel offset inside a group plane, smem pixel offset) of every band
+    // pixel, computed once so that the per-stage loader is a table walk with no index arithmetic
+    int2 *tbl = reinterpret_cast<int2 *>(sm + 2 * stage_px);
+    const int n_tbl = (p.RB + KS - 1) * p.W;
+    for (int idx = tid; idx < n_tbl; idx += kThreads) {
+        int s = idx / p.W, x = idx - s * p.W;
+        int Rr = R0 - PAD + s;
+        int2 e = make_int2(-1, 0);
+        if (Rr >= 0 && Rr < rows_total) {
+            int ff = Rr / p.H, yy = Rr - ff * p.H;
+            e.x = (int)(ff * (p.in_frame_stride >> 2)) + yy * p.W + x;
+            e.y = s * p.PW + PAD + x;
+        }
+        tbl[idx] = e;
+    }
     __syncthreads();
 
-    const int16_t *in = static_cast<const int16_t *>(p.in);
+    const uint2 *in_px = static_cast<const uint2 *>(p.in);
     const uint2 *wsrc = static_cast<const uint2 *>(p.w) + (size_t)mb * p.G * K2 * kCM;
 
     auto load_stage = [&](int st, int buf) {
@@ -124,20 +139,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
         const int ng = min(p.GS, p.G - g0);
         uint2 *wsm = sm + buf * stage_px;
         uint2 *xs = wsm + w_stage_px;
-        const int nrows = p.RB + KS - 1;
-        const int per_group = nrows * p.W;
-        for (int idx = tid; idx < ng * per_group; idx += kThreads) {
-            int gg = idx / per_group;
-            int rem = idx - gg * per_group;
-            int s = rem / p.W;
-            int x = rem - s * p.W;
-            int Rr = R0 - PAD + s;
-            if (Rr >= 0 && Rr < rows_total) {
-                int ff = Rr / p.H, yy = Rr - ff * p.H;
-                const int16_t *src = in + (size_t)ff * p.in_frame_stride +
-                                     (((size_t)(g0 + gg) * p.H + yy) * p.W + x) * 4;
-                cp_async8(xs + (gg * xrows + s) * p.PW + PAD + x, src);
-            }
+        const int plane = p.H * p.W;
+        for (int idx = tid; idx < n_tbl; idx += kThreads) {
+            const int2 e = tbl[idx];
+            if (e.x < 0) continue;
+            const uint2 *src = in_px + e.x + (size_t)g0 * plane;
+            uint2 *dst = xs + e.y;
+            for (int gg = 0; gg < ng; ++gg) cp_async8(dst + gg * xrows * p.PW, src + (size_t)gg * plane);
         }
         const uint2 *wg = wsrc + (size_t)g0 * K2 * kCM;
         const int nw16 = ng * K2 * kCM / 2;  // 16-byte chunks
@@ -350,12 +358,15 @@ size_t conv_fast_plan(ConvFastParams &p, int ksize, int elem_bytes)
     p.PW = pick_pitch(sw * tp + ksize - 1, tp, sw, px_bytes / 4);
     const int xrows = p.RB + ksize - 1 + 1;
     const size_t per_group = ((size_t)xrows * p.PW + (size_t)ksize * ksize * kCM) * px_bytes;
-    int gs = (int)((48 * 1024) / per_group);
+    const size_t tbl_bytes = (size_t)(p.RB + ksize - 1) * p.W * 8;  // per-CTA copy table
+    // two CTAs per SM: keep 2 x (2 stages + table) under ~200 KB of the 227 KB
+    size_t budget = 100 * 1024 > tbl_bytes + 2 * per_group ? (100 * 1024 - tbl_bytes) / 2 : per_group;
+    int gs = (int)(budget / per_group);
     if (gs < 1) gs = 1;
     if (gs > 8) gs = 8;
     if (gs > p.G) gs = p.G;
     p.GS = gs;
-    size_t smem = 2 * per_group * gs + 64;
+    size_t smem = 2 * per_group * gs + 64 + tbl_bytes;
     if (smem > 200 * 1024) return 0;
     return smem;
 }
@@ -379,7 +390,8 @@ static int launch_i16_variant(const ConvFastParams &p, size_t smem, cudaStream_t
 int launch_conv_i16_fast(const ConvFastParams &p, int ksize, cudaStream_t st, const char **variant)
 {
     const int xrows = p.RB + ksize - 1 + 1;
-    const size_t smem = 2 * (((size_t)p.GS * ((size_t)xrows * p.PW + (size_t)ksize * ksize * kCM) + 1) & ~(size_t)1) * 8;
+    const size_t smem = 2 * (((size_t)p.GS * ((size_t)xrows * p.PW + (size_t)ksize * ksize * kCM) + 1) & ~(size_t)1) * 8 +
+                        (size_t)(p.RB + ksize - 1) * p.W * 8;  // + the copy table
     const int tp = p.TP;
     const bool scaled = p.so <= 22;
 #define Y2_VARIANT(TPV, KSV)                                                                                  \
