@@ -6,7 +6,7 @@
 
 A "step" is one pass of the whole datapath (quantise -> 23 conv / 5 pool / reorg / route -> region)
 over one batch of synthetic 416x416 frames.  Weak scaling: every GPU processes --frames-per-gpu
-frames per step (default 512: BASELINE configs[4]'s frame stream, 4096 frames per step at 8 GPUs); ranks are
+frames per step (default 728 = two wave-filling passes of 364; BASELINE configs[4] frame stream); ranks are
 independent (frames shard with no data-path collective) and NCCL only gathers the region tensors.
 Prints ONE JSON line on rank 0.
 """
@@ -143,8 +143,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-gpu", type=int, default=512)
-    ap.add_argument("--chunk", type=int, default=256, help="frames per device pass (arena size)")
+    ap.add_argument("--frames-per-gpu", type=int, default=728)
+    ap.add_argument("--chunk", type=int, default=0, help="frames per device pass; 0 = the wave-filling size from model.best_pass_size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes for the cpu_baseline leg (default min(cores,32))")
@@ -156,7 +156,7 @@ def main():
     import torch
     import torch.distributed as dist
     from yolo2_b200 import cfg as ycfg, weights as yw
-    from yolo2_b200.model import Yolo2Net
+    from yolo2_b200.model import Yolo2Net, best_pass_size
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -173,7 +173,8 @@ def main():
 
     net = ycfg.parse_network_cfg(cfg_text())
     pack = yw.synth_pack(net, "int16", seed=0, table="default")
-    y = Yolo2Net(net, pack, device=local, max_batch=min(args.chunk, B))
+    chunk = args.chunk if args.chunk > 0 else best_pass_size(net, 128, 400)
+    y = Yolo2Net(net, pack, device=local, max_batch=min(chunk, B))
     # run everything on one explicit torch stream so torch.cuda.Event brackets the library's launches
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)

@@ -358,6 +358,9 @@ struct yolo2cuda_net {
     void *d_input_c4 = nullptr;
     void *d_frames = nullptr;      // staging for forward_host: float [max_batch][c][h][w]
     void *d_region = nullptr;      // staging for forward_host
+    void *d_frames2[2] = {nullptr, nullptr}, *d_region2[2] = {nullptr, nullptr};   // double-buffered staging
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     void *d_wblob = nullptr, *d_bblob = nullptr;
     void *d_tmp_planar_in = nullptr, *d_tmp_planar_out = nullptr;  // generic-fallback / dump scratch
     size_t tmp_planar_elems = 0;
@@ -629,6 +632,13 @@ int yolo2cuda_net_destroy(yolo2cuda_net *net)
     cudaStreamSynchronize(net->ctx->stream);
     for (void *p : net->owned) cudaFree(p);
     for (auto ev : net->ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        if (net->ev_h2d[i]) cudaEventDestroy(net->ev_h2d[i]);
+        if (net->ev_comp[i]) cudaEventDestroy(net->ev_comp[i]);
+        if (net->ev_d2h[i]) cudaEventDestroy(net->ev_d2h[i]);
+    }
+    if (net->s_h2d) cudaStreamDestroy(net->s_h2d);
+    if (net->s_d2h) cudaStreamDestroy(net->s_d2h);
     delete net;
     return YOLO2CUDA_SUCCESS;
 }
@@ -744,18 +754,48 @@ int yolo2cuda_net_forward_host(yolo2cuda_net *net, const float *frames, int batc
     cudaStream_t st = ctx->stream;
     const size_t frame_elems = (size_t)net->in_c * net->in_h * net->in_w;
     int rc;
+    // Double-buffered passes: the H2D copy of pass k+1 and the D2H copy of pass k-1 run on their own
+    // streams (separate DMA engines) while pass k computes on the context stream.
     if (!net->d_frames) {
-        if ((rc = net_alloc(net, &net->d_frames, frame_elems * net->max_batch * sizeof(float)))) return rc;
-        if ((rc = net_alloc(net, &net->d_region, net->region_outputs * net->max_batch * sizeof(float)))) return rc;
+        for (int i = 0; i < 2; ++i) {
+            if ((rc = net_alloc(net, &net->d_frames2[i], frame_elems * net->max_batch * sizeof(float)))) return rc;
+            if ((rc = net_alloc(net, &net->d_region2[i], net->region_outputs * net->max_batch * sizeof(float)))) return rc;
+            CUDA_OK(ctx, cudaEventCreateWithFlags(&net->ev_h2d[i], cudaEventDisableTiming));
+            CUDA_OK(ctx, cudaEventCreateWithFlags(&net->ev_comp[i], cudaEventDisableTiming));
+            CUDA_OK(ctx, cudaEventCreateWithFlags(&net->ev_d2h[i], cudaEventDisableTiming));
+        }
+        CUDA_OK(ctx, cudaStreamCreateWithFlags(&net->s_h2d, cudaStreamNonBlocking));
+        CUDA_OK(ctx, cudaStreamCreateWithFlags(&net->s_d2h, cudaStreamNonBlocking));
+        net->d_frames = net->d_frames2[0];
+        net->d_region = net->d_region2[0];
     }
-    for (int b0 = 0; b0 < batch; b0 += net->max_batch) {
-        int B = batch - b0 < net->max_batch ? batch - b0 : net->max_batch;
-        CUDA_OK(ctx, cudaMemcpyAsync(net->d_frames, frames + (size_t)b0 * frame_elems, frame_elems * B * sizeof(float),
-                                     cudaMemcpyHostToDevice, st));
-        if ((rc = forward_chunk(net, (const float *)net->d_frames, B, (float *)net->d_region))) return rc;
-        CUDA_OK(ctx, cudaMemcpyAsync(region_out + (size_t)b0 * net->region_outputs, net->d_region,
-                                     net->region_outputs * B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    const int npass = (batch + net->max_batch - 1) / net->max_batch;
+    auto pass_frames = [&](int k) { return (k + 1) * net->max_batch <= batch ? net->max_batch : batch - k * net->max_batch; };
+    auto issue_h2d = [&](int k) -> int {
+        const int buf = k & 1;
+        if (k >= 2) CUDA_OK(ctx, cudaStreamWaitEvent(net->s_h2d, net->ev_comp[buf], 0));   // pass k-2 has consumed this buffer
+        CUDA_OK(ctx, cudaMemcpyAsync(net->d_frames2[buf], frames + (size_t)k * net->max_batch * frame_elems,
+                                     frame_elems * pass_frames(k) * sizeof(float), cudaMemcpyHostToDevice, net->s_h2d));
+        CUDA_OK(ctx, cudaEventRecord(net->ev_h2d[buf], net->s_h2d));
+        return YOLO2CUDA_SUCCESS;
+    };
+    // order the side streams after whatever the caller queued on the context stream before this call
+    CUDA_OK(ctx, cudaEventRecord(net->ev_comp[0], st));
+    CUDA_OK(ctx, cudaStreamWaitEvent(net->s_h2d, net->ev_comp[0], 0));
+    if ((rc = issue_h2d(0))) return rc;
+    for (int k = 0; k < npass; ++k) {
+        const int buf = k & 1, B = pass_frames(k);
+        if (k + 1 < npass && (rc = issue_h2d(k + 1))) return rc;
+        CUDA_OK(ctx, cudaStreamWaitEvent(st, net->ev_h2d[buf], 0));
+        if (k >= 2) CUDA_OK(ctx, cudaStreamWaitEvent(st, net->ev_d2h[buf], 0));               // region buffer drained
+        if ((rc = forward_chunk(net, (const float *)net->d_frames2[buf], B, (float *)net->d_region2[buf]))) return rc;
+        CUDA_OK(ctx, cudaEventRecord(net->ev_comp[buf], st));
+        CUDA_OK(ctx, cudaStreamWaitEvent(net->s_d2h, net->ev_comp[buf], 0));
+        CUDA_OK(ctx, cudaMemcpyAsync(region_out + (size_t)k * net->max_batch * net->region_outputs, net->d_region2[buf],
+                                     net->region_outputs * B * sizeof(float), cudaMemcpyDeviceToHost, net->s_d2h));
+        CUDA_OK(ctx, cudaEventRecord(net->ev_d2h[buf], net->s_d2h));
     }
+    CUDA_OK(ctx, cudaStreamSynchronize(net->s_d2h));
     CUDA_OK(ctx, cudaStreamSynchronize(st));
     return YOLO2CUDA_SUCCESS;
 }

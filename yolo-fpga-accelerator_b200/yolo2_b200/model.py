@@ -128,3 +128,27 @@ def yolov2_cuda_ps(net: _cfg.Network, input: np.ndarray, pack: WeightsPack, devi
         return y.forward(np.asarray(input, np.float32).reshape(1, net.c, net.h, net.w))[0]
     finally:
         y.close()
+
+
+def best_pass_size(net: _cfg.Network, lo: int = 128, hi: int = 400, sms: int = 148, ctas_per_sm: int = 2) -> int:
+    """Frames per device pass that fills the conv grids' last wave best.
+
+    A conv launch has ceil(pass*H / (64 // (W/13))) bands x ceil(OFM/16) CTAs of equal cost (csrc/conv_i16.cu)
+    and sms*ctas_per_sm CTAs run at a time, so the pass size decides how full the last wave of each layer
+    is.  Returns the size in [lo, hi] maximising the step-weighted average of waves/ceil(waves)."""
+    import math
+    convs = [l for l in net.layers if l.type == _cfg.CONV]
+    slots = sms * ctas_per_sm
+
+    def eff(n):
+        ideal = real = 0.0
+        for l in convs:
+            tp = 13 if l.w % 13 == 0 else 7
+            sw = -(-l.w // tp)
+            rb = max(1, 64 // sw)
+            ctas = math.ceil(n * l.h / rb) * math.ceil(l.n / 16)
+            cost = math.ceil(l.c / 4) * l.size * l.size
+            ideal += ctas / slots * cost
+            real += math.ceil(ctas / slots) * cost
+        return ideal / real
+    return max(range(lo, hi + 1), key=lambda n: (round(eff(n), 4), -n))
