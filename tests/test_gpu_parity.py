@@ -319,3 +319,37 @@ def test_layer_dev_entry_matches_host_entry(accel16, oracle):
         "IsBN", "TM", "TN", "TR", "TC", "OFM_num_bound", "mLoopsxTM", "mLoops_a1xTM", "LayerType")], *q)
     accel16.synchronize()
     assert np.array_equal(valid(dout.cpu().numpy(), 26), valid(want, 26))
+
+
+# ---- experimental tensor-core (tcgen05 + TMEM) conv path: opt-in with YOLO2CUDA_TC=1 ---------------
+
+@pytest.fixture()
+def accel16_tc(monkeypatch):
+    from yolo2_b200.accel import Accelerator
+    monkeypatch.setenv("YOLO2CUDA_TC", "1")
+    a = Accelerator(0, "int16")
+    yield a
+    a.close()
+
+
+@pytest.mark.parametrize("c,n,k,w,h,q,amp", [
+    (4, 128, 1, 8, 8, (14, 10, 10, 10), 600), (64, 128, 3, 13, 13, (14, 10, 10, 10), 600),
+    (64, 200, 3, 26, 26, (13, 9, 12, 7), 600), (256, 256, 3, 13, 13, (15, 12, 8, 10), 600),
+    (96, 40, 1, 19, 19, (12, 12, 7, 8), 600), (17, 33, 3, 20, 11, (13, 9, 12, 7), 32767),
+    (20, 130, 3, 21, 9, (4, 10, 6, 12), 32767), (36, 64, 3, 13, 13, (15, 15, 8, 0), 3000)])
+def test_tensor_core_conv_bit_exact(c, n, k, w, h, q, amp, accel16_tc, oracle):
+    """tcgen05.mma kind::i8 on hi/lo byte planes with a block-diagonal activation operand (7 chain steps per
+    K=32 slice), recombined per step on the CUDA cores: same bits as the reference, incl. saturation."""
+    a, x, wr, b, _ = make_conv_case(c * n + k, c, n, k, 1, w, h, 1, amp=amp, xamp=32767 if amp > 600 else 2000)
+    want = oracle_conv(oracle, a, x, wr, b, q)
+    got = accel_call(accel16_tc, a, x, wr, b, q)
+    assert accel16_tc.last_kernel.startswith("conv_i16_tc<")
+    assert np.array_equal(valid(got, w), valid(want, w))
+
+
+def test_tensor_core_net_bit_exact(monkeypatch, oracle):
+    monkeypatch.setenv("YOLO2CUDA_TC", "1")
+    monkeypatch.setenv("YOLO2CUDA_TC_MIN_OFM", "8")
+    net, pack = _net_case(416, 416, 3, 8, "stress", seed=11)
+    frames = yw.synth_frames(net, 3, seed=2000)
+    _check_net(net, pack, frames, oracle, max_batch=2)

@@ -25,6 +25,8 @@ struct yolo2cuda_ctx {
     uint64_t launches = 0;
     const char *last_kernel = "";
     int force_generic = 0;
+    int use_tc = 0;   // YOLO2CUDA_TC=1: tcgen05 conv (csrc/conv_i16_tc.cu) where eligible
+    int tc_min_ofm = 96;
     // growable device scratch for the per-layer entry points
     struct Scratch { void *p = nullptr; size_t bytes = 0; } s_in, s_out, s_w, s_b, s_c4in, s_c4out, s_wprep;
 };
@@ -132,8 +134,20 @@ int run_conv_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, cons
     int rc;
     if ((rc = ensure(ctx, ctx->s_c4in, c4_elems(IFM, Ih, Iw) * ctx->elem))) return rc;
     if ((rc = ensure(ctx, ctx->s_c4out, c4_elems(OFM, Oh, Ow) * ctx->elem))) return rc;
-    if ((rc = ensure(ctx, ctx->s_wprep, wprep_bytes(IFM, OFM, K, ctx->elem)))) return rc;
+    const bool tc = ctx->use_tc && ctx->elem == 2 && so >= 8 && so <= 22;
+    if ((rc = ensure(ctx, ctx->s_wprep, tc ? wprep_tc_bytes(IFM, OFM, K) : wprep_bytes(IFM, OFM, K, ctx->elem)))) return rc;
     launch_planar_to_c4(Input, ctx->s_c4in.p, 1, IFM, Ih, Iw, 0, 0, ctx->elem, st);
+    if (tc) {
+        launch_wprep_tc((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, so, st);
+        p.in = ctx->s_c4in.p; p.out = ctx->s_c4out.p; p.w = ctx->s_wprep.p; p.bias = Beta;
+        p.in_frame_stride = 0; p.out_frame_stride = 0;
+        p.so = so; p.sb = sb; p.leaky = IsNL;
+        if (launch_conv_i16_tc(p, K, st, &ctx->last_kernel) < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "tc conv not eligible");
+        launch_c4_to_planar(ctx->s_c4out.p, Output, 1, OFM, Oh, Ow, 0, 0, ctx->elem, st);
+        ctx->launches += 4;
+        CUDA_OK(ctx, cudaGetLastError());
+        return YOLO2CUDA_SUCCESS;
+    }
     if (ctx->elem == 2) launch_wprep_i16((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, st);
     else launch_wprep_f32((const float *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, st);
     p.in = ctx->s_c4in.p; p.out = ctx->s_c4out.p; p.w = ctx->s_wprep.p; p.bias = Beta;
@@ -179,6 +193,9 @@ int yolo2cuda_create(yolo2cuda_ctx **out, int device, int precision)
     ctx->stream = ctx->own_stream;
     const char *fg = getenv("YOLO2CUDA_FORCE_GENERIC");
     ctx->force_generic = (fg && fg[0] && fg[0] != '0') ? 1 : 0;
+    const char *tc = getenv("YOLO2CUDA_TC");
+    ctx->use_tc = (tc && tc[0] && tc[0] != '0') ? 1 : 0;
+    if (const char *mo = getenv("YOLO2CUDA_TC_MIN_OFM")) ctx->tc_min_ofm = atoi(mo);
     *out = ctx;
     return YOLO2CUDA_SUCCESS;
 }
@@ -342,6 +359,8 @@ struct LayerPlan {
     int conv_index = -1;
     size_t w_off = 0, b_off = 0;   // element offsets into the reference blobs
     void *w_dev = nullptr;         // device weight layout (fast path)
+    void *w_tc = nullptr;          // tcgen05 operand tiles (tensor-core path)
+    bool tc = false;
     int Qw = 0, Qa_in = 0, Qa_out = 0, Qb = 0;
     int reorg_shift = 0;
     int region_q = 0;
@@ -417,7 +436,13 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
             if (l.fast) {
                 ConvFastParams p = l.cp;
                 p.B = B;
-                int n = e == 2 ? launch_conv_i16_fast(p, l.d.size, st, &l.variant) : launch_conv_f32_fast(p, l.d.size, st, &l.variant);
+                int n;
+                if (l.tc) {
+                    p.w = l.w_tc;
+                    n = launch_conv_i16_tc(p, l.d.size, st, &l.variant);
+                } else {
+                    n = e == 2 ? launch_conv_i16_fast(p, l.d.size, st, &l.variant) : launch_conv_f32_fast(p, l.d.size, st, &l.variant);
+                }
                 if (n < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "layer %zu: no fast conv variant", i);
                 launches += n;
                 ctx->last_kernel = l.variant;
@@ -709,6 +734,13 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                     p.in_frame_stride = l.in.frame_stride; p.out_frame_stride = l.out.frame_stride;
                     p.so = so > 30 ? 30 : so; p.sb = l.Qb - l.Qa_out; p.leaky = l.d.leaky;
                     l.cp = p;
+                    // tensor-core path: wide layers only (a CTA covers 128 output channels)
+                    l.tc = ctx->use_tc && e == 2 && so >= 8 && so <= 22 && l.d.n >= ctx->tc_min_ofm;
+                    if (l.tc) {
+                        if (!l.w_tc && (rc = net_alloc(net, &l.w_tc, wprep_tc_bytes(l.d.c, l.d.n, l.d.size)))) return rc;
+                        launch_wprep_tc((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, so, st);
+                        ctx->launches += 1;
+                    }
                 }
             }
         } else if (l.d.type == YOLO2CUDA_REORG) {

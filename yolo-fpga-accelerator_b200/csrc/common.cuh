@@ -103,3 +103,10 @@ void launch_region(const void *in, float *out, int B, int w, int h, int n, int c
                    int elem_bytes, cudaStream_t st);
 
 }  // namespace y2
+
+namespace y2 {
+// tensor-core (tcgen05) int16 conv, csrc/conv_i16_tc.cu
+size_t wprep_tc_bytes(int ifm, int ofm, int ksize);
+void launch_wprep_tc(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, int so, cudaStream_t st);
+int launch_conv_i16_tc(const ConvFastParams &p, int ksize, cudaStream_t st, const char **variant);
+}  // namespace y2
