@@ -1,5 +1,5 @@
 import os, sys, numpy as np
-os.environ["YOLO2CUDA_TC"] = "1"
+os.environ.setdefault("YOLO2CUDA_TC", "1")
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/yolo-fpga-accelerator_b200"); sys.path.insert(0, "/root/repo/tests")
 from helpers import make_conv_case, oracle_conv, accel_call, valid
 from oracle.oracle import Oracle

@@ -135,14 +135,16 @@ int run_conv_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, cons
     if ((rc = ensure(ctx, ctx->s_c4in, c4_elems(IFM, Ih, Iw) * ctx->elem))) return rc;
     if ((rc = ensure(ctx, ctx->s_c4out, c4_elems(OFM, Oh, Ow) * ctx->elem))) return rc;
     const bool tc = ctx->use_tc && ctx->elem == 2 && so >= 8 && so <= 22;
-    if ((rc = ensure(ctx, ctx->s_wprep, tc ? wprep_tc_bytes(IFM, OFM, K) : wprep_bytes(IFM, OFM, K, ctx->elem)))) return rc;
+    const bool tc2 = tc && ctx->use_tc == 2;
+    if ((rc = ensure(ctx, ctx->s_wprep, tc2 ? wprep_tc2_bytes(IFM, OFM, K) : tc ? wprep_tc_bytes(IFM, OFM, K) : wprep_bytes(IFM, OFM, K, ctx->elem)))) return rc;
     launch_planar_to_c4(Input, ctx->s_c4in.p, 1, IFM, Ih, Iw, 0, 0, ctx->elem, st);
     if (tc) {
-        launch_wprep_tc((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, so, st);
+        if (tc2) launch_wprep_tc2((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, so, st);
+        else launch_wprep_tc((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, so, st);
         p.in = ctx->s_c4in.p; p.out = ctx->s_c4out.p; p.w = ctx->s_wprep.p; p.bias = Beta;
         p.in_frame_stride = 0; p.out_frame_stride = 0;
         p.so = so; p.sb = sb; p.leaky = IsNL;
-        if (launch_conv_i16_tc(p, K, st, &ctx->last_kernel) < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "tc conv not eligible");
+        if ((tc2 ? launch_conv_i16_tc2(p, K, st, &ctx->last_kernel) : launch_conv_i16_tc(p, K, st, &ctx->last_kernel)) < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "tc conv not eligible");
         launch_c4_to_planar(ctx->s_c4out.p, Output, 1, OFM, Oh, Ow, 0, 0, ctx->elem, st);
         ctx->launches += 4;
         CUDA_OK(ctx, cudaGetLastError());
@@ -194,7 +196,7 @@ int yolo2cuda_create(yolo2cuda_ctx **out, int device, int precision)
     const char *fg = getenv("YOLO2CUDA_FORCE_GENERIC");
     ctx->force_generic = (fg && fg[0] && fg[0] != '0') ? 1 : 0;
     const char *tc = getenv("YOLO2CUDA_TC");
-    ctx->use_tc = (tc && tc[0] && tc[0] != '0') ? 1 : 0;
+    ctx->use_tc = (tc && tc[0] && tc[0] != '0') ? (tc[0] == '2' ? 2 : 1) : 0;   // 1: csrc/conv_i16_tc.cu, 2: csrc/conv_i16_tc2.cu
     if (const char *mo = getenv("YOLO2CUDA_TC_MIN_OFM")) ctx->tc_min_ofm = atoi(mo);
     *out = ctx;
     return YOLO2CUDA_SUCCESS;
@@ -439,7 +441,7 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
                 int n;
                 if (l.tc) {
                     p.w = l.w_tc;
-                    n = launch_conv_i16_tc(p, l.d.size, st, &l.variant);
+                    n = ctx->use_tc == 2 ? launch_conv_i16_tc2(p, l.d.size, st, &l.variant) : launch_conv_i16_tc(p, l.d.size, st, &l.variant);
                 } else {
                     n = e == 2 ? launch_conv_i16_fast(p, l.d.size, st, &l.variant) : launch_conv_f32_fast(p, l.d.size, st, &l.variant);
                 }
@@ -737,8 +739,10 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                     // tensor-core path: wide layers only (a CTA covers 128 output channels)
                     l.tc = ctx->use_tc && e == 2 && so >= 8 && so <= 22 && l.d.n >= ctx->tc_min_ofm;
                     if (l.tc) {
-                        if (!l.w_tc && (rc = net_alloc(net, &l.w_tc, wprep_tc_bytes(l.d.c, l.d.n, l.d.size)))) return rc;
-                        launch_wprep_tc((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, so, st);
+                        const bool v2 = ctx->use_tc == 2;
+                        if (!l.w_tc && (rc = net_alloc(net, &l.w_tc, v2 ? wprep_tc2_bytes(l.d.c, l.d.n, l.d.size) : wprep_tc_bytes(l.d.c, l.d.n, l.d.size)))) return rc;
+                        if (v2) launch_wprep_tc2((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, so, st);
+                        else launch_wprep_tc((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, so, st);
                         ctx->launches += 1;
                     }
                 }

@@ -27,7 +27,8 @@ class LayerDesc(C.Structure):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(_HERE), "lib", "libyolo2cuda.so")
+    # YOLO2CUDA_LIB: development override (e.g. a build with -DY2_TC2_PROFILE); still a CUDA library, never a fallback
+    return os.environ.get("YOLO2CUDA_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libyolo2cuda.so")
 
 
 _LAYER_ARGS = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 23
