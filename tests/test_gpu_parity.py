@@ -321,13 +321,14 @@ def test_layer_dev_entry_matches_host_entry(accel16, oracle):
     assert np.array_equal(valid(dout.cpu().numpy(), 26), valid(want, 26))
 
 
-# ---- experimental tensor-core (tcgen05 + TMEM) conv path: opt-in with YOLO2CUDA_TC=1 ---------------
+# ---- tensor-core (tcgen05 + TMEM) conv paths: opt-in with YOLO2CUDA_TC=1 (csrc/conv_i16_tc.cu) or 2 (csrc/conv_i16_tc2.cu) ------
 
-@pytest.fixture()
-def accel16_tc(monkeypatch):
+@pytest.fixture(params=["1", "2"])
+def accel16_tc(request, monkeypatch):
     from yolo2_b200.accel import Accelerator
-    monkeypatch.setenv("YOLO2CUDA_TC", "1")
+    monkeypatch.setenv("YOLO2CUDA_TC", request.param)
     a = Accelerator(0, "int16")
+    a.tc_version = request.param
     yield a
     a.close()
 
@@ -343,12 +344,32 @@ def test_tensor_core_conv_bit_exact(c, n, k, w, h, q, amp, accel16_tc, oracle):
     a, x, wr, b, _ = make_conv_case(c * n + k, c, n, k, 1, w, h, 1, amp=amp, xamp=32767 if amp > 600 else 2000)
     want = oracle_conv(oracle, a, x, wr, b, q)
     got = accel_call(accel16_tc, a, x, wr, b, q)
-    assert accel16_tc.last_kernel.startswith("conv_i16_tc<")
+    assert accel16_tc.last_kernel.startswith("conv_i16_tc<" if accel16_tc.tc_version == "1" else "conv_i16_tc2<")
     assert np.array_equal(valid(got, w), valid(want, w))
 
 
-def test_tensor_core_net_bit_exact(monkeypatch, oracle):
-    monkeypatch.setenv("YOLO2CUDA_TC", "1")
+@pytest.mark.parametrize("so", list(range(8, 23)))
+def test_tensor_core_v2_every_shift(so, monkeypatch, oracle):
+    """csrc/conv_i16_tc2.cu instantiates one kernel per accumulator shift (the step's LEA.HI takes an immediate) and switches
+    formula at so = 17 and the rounding-constant plane at so = 16: every instantiation, full-range operands (saturation)."""
+    from yolo2_b200.accel import Accelerator
+    monkeypatch.setenv("YOLO2CUDA_TC", "2")
+    acc = Accelerator(0, "int16")
+    try:
+        q = (so - 2, 10, 8, 9)                      # Qw, Qa_in, Qa_out, Qb -> shift_out = Qa_in + Qw - Qa_out = so
+        for (c, n, k, w, h) in ((24, 130, 3, 13, 13), (60, 128, 1, 7, 5)):
+            a, x, wr, b, _ = make_conv_case(so * 100 + c, c, n, k, 1, w, h, 1, amp=32767, xamp=32767)
+            want = oracle_conv(oracle, a, x, wr, b, q)
+            got = accel_call(acc, a, x, wr, b, q)
+            assert acc.last_kernel.startswith("conv_i16_tc2<")
+            assert np.array_equal(valid(got, w), valid(want, w))
+    finally:
+        acc.close()
+
+
+@pytest.mark.parametrize("tc", ["1", "2"])
+def test_tensor_core_net_bit_exact(tc, monkeypatch, oracle):
+    monkeypatch.setenv("YOLO2CUDA_TC", tc)
     monkeypatch.setenv("YOLO2CUDA_TC_MIN_OFM", "8")
     net, pack = _net_case(416, 416, 3, 8, "stress", seed=11)
     frames = yw.synth_frames(net, 3, seed=2000)

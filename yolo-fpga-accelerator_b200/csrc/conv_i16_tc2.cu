@@ -179,8 +179,6 @@ __host__ __device__ inline int operand_off(int row, int k) { return (((row >> 3)
 
 #ifdef Y2_TC2_PROFILE
 __device__ long long g_tc2_prof[20 * 8];
-__device__ long long g_tc2_tl[48 * 16];   // [tile - 600][event]: 0 issuer passed go, 1 issue done, 2..5 epilogue warp q passed mma_done, 6..9 loaded+released, 10..13 computed
-#define PROF_TL(tile, ev) do { if (blockIdx.x == 1 && blockIdx.y == 0 && lane == 0 && (tile) >= 600 && (tile) < 648) g_tc2_tl[((tile) - 600) * 16 + (ev)] = clock64(); } while (0)
 #define PROF_DECL long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_ = clock64(); const long long pstart_ = pt_;
 #define PROF_ADD(i) do { long long n_ = clock64(); prof_[i] += n_ - pt_; pt_ = n_; } while (0)
 #define PROF_END do { prof_[7] = clock64() - pstart_; if (blockIdx.x == 1 && blockIdx.y == 0 && lane == 0) for (int i_ = 0; i_ < 8; ++i_) g_tc2_prof[warp * 8 + i_] = prof_[i_]; } while (0)
@@ -188,7 +186,6 @@ __device__ long long g_tc2_tl[48 * 16];   // [tile - 600][event]: 0 issuer passe
 #define PROF_DECL
 #define PROF_ADD(i)
 #define PROF_END
-#define PROF_TL(tile, ev)
 #endif
 
 struct Tc2Params {
@@ -311,28 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                     bulk_g2s(sW + b * kWBytes, wsrc + (size_t)b * kWBytes, kWBytes, &w_full[b]);
                 }
             }
-            // copy one K-block of weights shared memory -> registers -> tensor memory (A operand slot bn & 1): issuer warp iw owns
-            // TMEM lane quadrant iw (= warp % 4).  Done in the middle of K-block bn-1, when the MMAs of block bn-2 (the slot's
-            // previous readers) have long completed, so none of the waits in here blocks and the epilogue never stalls on weights.
-            const int row = iw * 32 + lane;
-            const unsigned lane_base = tmem + ((unsigned)(iw * 32) << 16);
-            auto stage_weights = [&](int bn) {
-                const int s = bn % kWRing, a = bn & 1;
-                mbar_wait(&w_full[s], (bn / kWRing) & 1);
-                const uint4 *src = reinterpret_cast<const uint4 *>(sW + s * kWBytes + row * 64);
-                const int sw = (row >> 1) & 3;
-                const uint4 c0 = src[0 ^ sw], c1 = src[1 ^ sw], c2 = src[2 ^ sw], c3 = src[3 ^ sw];
-                if (bn >= 2) mbar_wait(&a_empty[a], ((bn >> 1) - 1) & 1);   // the MMAs of block bn-2 have read this slot
-                asm volatile("tcgen05.fence::after_thread_sync;");
-                tmem_st8(lane_base + kACol + a * 16, c0, c1);
-                tmem_st8(lane_base + kACol + a * 16 + 8, c2, c3);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;");
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(&w_empty[s]); mbar_arrive(&a_full[a]); }
-            };
             PROF_DECL
-            stage_weights(0);
             int tb = iw;                                     // TMEM buffer it % 5 of this warp's next tile
             for (int b = 0; b < p.nkb; ++b) {
                 PROF_ADD(4);
@@ -351,7 +327,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                     const int r = iw + j * kIssuers;
                     mbar_wait(&go[r], b & 1);
                     PROF_ADD(1);
-                    PROF_TL(b * kR + r, 0);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     if (elected) {
                         const unsigned long long dBh = dB0 + r * kBStep, dBl = dBh + kBPlane;
@@ -366,11 +341,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                     __syncwarp();
                     tb = tb >= kBufs - kIssuers ? tb - (kBufs - kIssuers) : tb + kIssuers;
                     PROF_ADD(3);
-                    PROF_TL(b * kR + r, 1);
-                    if (j == 0 && b + 1 < p.nkb) {
-                        stage_weights(b + 1);
-                        PROF_ADD(5);
-                    }
                 }
             }
             PROF_END;
@@ -463,7 +433,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
         // ===== epilogue warps: thread = one output channel (TMEM lane); warp group kg = warp/4 takes the tiles r = kg (mod 3) =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
         const int q4 = warp & 3, kg = warp >> 2;
-        const int m = mtile * kM + q4 * 32 + lane;
+        const int row = q4 * 32 + lane;
+        const int m = mtile * kM + row;
         const unsigned lane_base = tmem + ((unsigned)(q4 * 32) << 16);
         int U[kR / 3][kPx];
         {
@@ -478,61 +449,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
 #pragma unroll
                 for (int j = 0; j < kPx; ++j) U[r][j] = (int)boff;
         }
-        // A tile is read out in two halves (steps 0-3: 16 columns, steps 4-6: 12 columns) into two register sets, software
-        // pipelined: while one half is being computed the other half (of this tile, then of the group's next tile) is in flight
-        // from tensor memory, and the probe of the next tile's barrier is issued before the compute that hides its latency.
-        asm volatile(".reg .pred y2_ptest;");
-        int ah_[16], am_[16], al_[16], bh_[16], bm_[16], bl_[16];
+        // copy one K-block of weights shared memory -> registers -> tensor memory (A operand slot bn & 1)
+        auto stage_weights = [&](int bn) {
+            const int s = bn % kWRing, a = bn & 1;
+            mbar_wait(&w_full[s], (bn / kWRing) & 1);
+            const uint4 *src = reinterpret_cast<const uint4 *>(sW + s * kWBytes + row * 64);
+            const int sw = (row >> 1) & 3;
+            const uint4 c0 = src[0 ^ sw], c1 = src[1 ^ sw], c2 = src[2 ^ sw], c3 = src[3 ^ sw];
+            if (bn >= 2) mbar_wait(&a_empty[a], ((bn >> 1) - 1) & 1);   // the MMAs of block bn-2 have read this slot
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            tmem_st8(lane_base + kACol + a * 16, c0, c1);
+            tmem_st8(lane_base + kACol + a * 16 + 8, c2, c3);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&w_empty[s]); mbar_arrive(&a_full[a]); }
+        };
         PROF_DECL
-        int tb = kg;                                // TMEM buffer it % 5 of this group's current tile (stride 3)
-        mbar_wait(&mma_done[kg], 0);
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        tmem_ld16(lane_base + tb * kBufCols, ah_); tmem_ld16(lane_base + tb * kBufCols + kN, am_); tmem_ld16(lane_base + tb * kBufCols + 2 * kN, al_);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        reg_fence16(ah_); reg_fence16(am_); reg_fence16(al_);
+        if (kg == 0) stage_weights(0);
+        int tb = kg;                                // TMEM buffer it % 5 of this group's next tile (stride 3)
         for (int b = 0; b < p.nkb; ++b) {
+            PROF_ADD(4);
+            if (b + 1 < p.nkb && (b + 1) % 3 == kg) stage_weights(b + 1);
+            PROF_ADD(0);
 #pragma unroll
             for (int rr = 0; rr < kR / 3; ++rr) {
                 const int r = 3 * rr + kg;
-                const unsigned base = lane_base + tb * kBufCols;
                 PROF_ADD(4);
-                tmem_ld16(base + 16, bh_); tmem_ld16(base + kN + 16, bm_); tmem_ld16(base + 2 * kN + 16, bl_);
-                // the group's next tile
-                const int rn = rr < kR / 3 - 1 ? r + 3 : kg, bn = rr < kR / 3 - 1 ? b : b + 1;
-                const bool more = bn < p.nkb;
-                const int tbn = tb >= 2 ? tb - 2 : tb + 3;
-                if (more) asm volatile("mbarrier.test_wait.parity.shared::cta.b64 y2_ptest, [%0], %1;" ::"r"(smem_u32(&mma_done[rn])), "r"((unsigned)(bn & 1)) : "memory");
-#pragma unroll
-                for (int n = 0; n < 16; ++n) U[rr][n % kPx] = tc2_step<SO>(U[rr][n % kPx], ah_[n], am_[n], al_[n]);
-                PROF_ADD(3);
+                mbar_wait(&mma_done[r], b & 1);
+                PROF_ADD(1);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const unsigned base = lane_base + tb * kBufCols;
+                int hh[32], mm[32], ll[32];      // column n = step*4 + pixel
+                tmem_ld16(base, hh); tmem_ld16(base + 16, hh + 16);
+                tmem_ld16(base + kN, mm); tmem_ld16(base + kN + 16, mm + 16);
+                tmem_ld16(base + 2 * kN, ll); tmem_ld16(base + 2 * kN + 16, ll + 16);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                reg_fence16(bh_); reg_fence16(bm_); reg_fence16(bl_);
-                // the whole tile is in registers: tile it+5 (ring slot r+5 mod 12) may overwrite this TMEM buffer
+                reg_fence16(hh); reg_fence16(hh + 16); reg_fence16(mm); reg_fence16(mm + 16); reg_fence16(ll); reg_fence16(ll + 16);
+                // everything is in registers: tile it+5 (ring slot r+5 mod 12) may overwrite this TMEM buffer
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&go[r + kBufs < kR ? r + kBufs : r + kBufs - kR]);
                 PROF_ADD(2);
-                PROF_TL(b * kR + r, 6 + q4);
-                if (more) {
-                    unsigned ok;
-                    asm volatile("selp.u32 %0, 1, 0, y2_ptest;" : "=r"(ok)::"memory");
-                    if (!ok) mbar_wait(&mma_done[rn], bn & 1);
-                    PROF_ADD(1);
-                    PROF_TL(bn * kR + rn, 2 + q4);
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-                    const unsigned basen = lane_base + tbn * kBufCols;
-                    tmem_ld16(basen, ah_); tmem_ld16(basen + kN, am_); tmem_ld16(basen + 2 * kN, al_);
-                }
 #pragma unroll
-                for (int n = 0; n < (kSteps - 4) * kPx; ++n) U[rr][n % kPx] = tc2_step<SO>(U[rr][n % kPx], bh_[n], bm_[n], bl_[n]);
+                for (int n = 0; n < kSteps * kPx; ++n) U[rr][n % kPx] = tc2_step<SO>(U[rr][n % kPx], hh[n], mm[n], ll[n]);
+                tb = tb >= 2 ? tb - 2 : tb + 3;
                 PROF_ADD(3);
-                PROF_TL(b * kR + r, 10 + q4);
-                if (more) {
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    reg_fence16(ah_); reg_fence16(am_); reg_fence16(al_);
-                }
-                tb = tbn;
-                PROF_ADD(2);
             }
         }
         PROF_END;
@@ -666,17 +628,6 @@ int launch_conv_i16_tc2(const ConvFastParams &cp, int ksize, cudaStream_t st, co
         long long h[20 * 8];
         cudaMemcpyFromSymbol(h, g_tc2_prof, sizeof(h));
         fprintf(stderr, "tc2 profile (CTA 1,0) G=%d W=%d nkb=%d: per warp [w_stage|wait a, wait b_full|mma_done, wait t_empty|ld, issue|compute, other, -, -, total]\n", cp.G, cp.W, p.nkb);
-        {
-            static long long tl[48 * 16];
-            cudaMemcpyFromSymbol(tl, g_tc2_tl, sizeof(tl));
-            long long t0 = tl[0];
-            fprintf(stderr, "timeline (cycles rel. to tile 600's go): tile | go-pass issue-done | mma_done-pass x4 | loaded x4 | computed x4\n");
-            for (int t = 0; t < 48 && p.nkb * kR > 648; ++t) {
-                fprintf(stderr, "  t%3d:", 600 + t);
-                for (int e = 0; e < 14; ++e) fprintf(stderr, "%s%7lld", (e == 2 || e == 6 || e == 10) ? " |" : "", tl[t * 16 + e] - t0);
-                fprintf(stderr, "\n");
-            }
-        }
         int hd[20 * 4], ab = 0;
         cudaMemcpyFromSymbol(hd, g_tc2_dbg, sizeof(hd));
         cudaMemcpyFromSymbol(&ab, g_tc2_abort, sizeof(ab));
