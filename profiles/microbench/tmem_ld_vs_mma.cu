@@ -28,7 +28,7 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, int *r)
 
 // warps 0..NR-1: readers (NR = 4, 8 or 12; quadrant = warp % 4); warps NR..NR+NI-1: MMA issuers with QD groups of 4 MMAs in flight each
 template <int NR, int NI, int QD>
-__global__ void __launch_bounds__((NR + NI) * 32, 1) k(long long *cycles, int *sink, int iters)
+__global__ void __launch_bounds__((NR + NI) * 32, 1) k(long long *cycles, int *sink, int iters, long long *mma_groups)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ unsigned tmem_base;
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__((NR + NI) * 32, 1) k(long long *cycles, int *s
             }
             __syncwarp();
             if (g >= QD - 1) mbar_wait(&bars[iw * 8 + ((g - (QD - 1)) & 7)], ((g - (QD - 1)) >> 3) & 1);
+            if (lane == 0) mma_groups[blockIdx.x * 4 + iw] = g + 1;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -95,15 +96,20 @@ void run(int nsm, long long *cyc, int *sink)
 {
     const int iters = 2000;
     cudaFuncSetAttribute(k<NR, NI, QD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
-    k<NR, NI, QD><<<nsm, (NR + NI) * 32, 120 * 1024>>>(cyc, sink, iters);
+    long long *mg; cudaMalloc(&mg, sizeof(long long) * 4 * nsm); cudaMemset(mg, 0, sizeof(long long) * 4 * nsm);
+    k<NR, NI, QD><<<nsm, (NR + NI) * 32, 120 * 1024>>>(cyc, sink, iters, mg);
     cudaError_t err = cudaDeviceSynchronize();
     long long h[2048];
     cudaMemcpy(h, cyc, sizeof(long long) * nsm * NR, cudaMemcpyDeviceToHost);
     double avg = 0;
     for (int i = 0; i < nsm * NR; ++i) avg += h[i];
     avg /= nsm * NR;
-    printf("{\"reader_warps\": %d, \"mma_warps\": %d, \"mma_groups_in_flight_per_warp\": %d, \"err\": \"%s\", \"cycles_per_tile_readout\": %.1f}\n", NR, NI, QD,
-           cudaGetErrorString(err), avg / iters);
+    long long hg[1024]; cudaMemcpy(hg, mg, sizeof(long long) * 4 * nsm, cudaMemcpyDeviceToHost);
+    double groups = 0; for (int i = 0; i < 4 * nsm; ++i) groups += hg[i];
+    groups /= nsm;   // 4-MMA groups per SM during the readers' run
+    printf("{\"reader_warps\": %d, \"mma_warps\": %d, \"mma_groups_in_flight_per_warp\": %d, \"err\": \"%s\", \"cycles_per_tile_readout\": %.1f, \"cycles_per_mma_per_sm\": %.1f}\n", NR, NI, QD,
+           cudaGetErrorString(err), avg / iters, groups > 0 ? avg / (groups * 4) : 0.0);
+    cudaFree(mg);
 }
 
 int main()
@@ -115,6 +121,6 @@ int main()
     run<4, 0, 1>(nsm, cyc, sink); run<12, 0, 1>(nsm, cyc, sink);
     run<4, 1, 1>(nsm, cyc, sink); run<4, 1, 4>(nsm, cyc, sink);
     run<4, 4, 1>(nsm, cyc, sink); run<4, 4, 2>(nsm, cyc, sink);
-    run<12, 4, 1>(nsm, cyc, sink); run<12, 4, 2>(nsm, cyc, sink); run<12, 2, 1>(nsm, cyc, sink);
+    run<12, 4, 1>(nsm, cyc, sink); run<12, 4, 2>(nsm, cyc, sink); run<12, 2, 1>(nsm, cyc, sink); run<8, 2, 2>(nsm, cyc, sink); run<8, 4, 2>(nsm, cyc, sink);
     return 0;
 }
