@@ -140,6 +140,16 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
 int yolo2cuda_net_forward_host(yolo2cuda_net *net, const float *frames, int batch, float *region_out);
 int yolo2cuda_net_forward_dev(yolo2cuda_net *net, const float *frames, int batch, float *region_out);
 
+/* Image front-end on the GPU: what load_image_stb + letterbox_image do on the host in the reference
+ * (src/core/yolo_image.cpp:178-187 u8 -> float/255, :84-127 two-pass bilinear resize, :146-165 letterbox with 0.5 fill),
+ * bit-exact.  src: u8 [batch][ih][iw][ic] interleaved (stbi_load's layout), every image the same size;
+ * dst: float [batch][ic][net_h][net_w].  DEVICE pointers, async on the stream. */
+int yolo2cuda_letterbox_dev(yolo2cuda_ctx *ctx, const unsigned char *src, int batch, int iw, int ih, int ic,
+                            float *dst, int net_w, int net_h);
+/* yolo2cuda_net_forward_host fed with raw images: HOST u8 [batch][ih][iw][in_c] -> letterbox on the GPU -> network. */
+int yolo2cuda_net_forward_images_host(yolo2cuda_net *net, const unsigned char *images, int batch, int iw, int ih,
+                                      float *region_out);
+
 /* Copies layer `layer`'s output feature map of frame `frame` (from the last forward) to the
  * HOST buffer `dst` in the reference layout [out_c][out_h][ceil8(out_w)] (int16_t or float). */
 int yolo2cuda_net_get_layer_output(yolo2cuda_net *net, int layer, int frame, void *dst, size_t dst_elems);

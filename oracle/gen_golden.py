@@ -103,5 +103,28 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)) >> 10, "KiB")
 
 
+LETTERBOX = [  # (image w, h, c, net_w, net_h): landscape, portrait, non-square net, upscale, one-pixel-wide, no-op size
+    (97, 61, 3, 64, 64), (61, 97, 3, 64, 64), (50, 50, 3, 64, 48), (20, 15, 3, 48, 48), (1, 5, 3, 8, 8), (32, 32, 1, 32, 32),
+    (160, 120, 3, 104, 104)]
+
+
+def gen_letterbox():
+    """letterbox_image of the unmodified reference (src/core/yolo_image.cpp:146-165) on seeded stb-layout u8 images."""
+    os.makedirs(OUT, exist_ok=True)
+    r16 = Ref("int16")
+    blob = {}
+    for i, (w, h, c, nw, nh) in enumerate(LETTERBOX):
+        img = np.random.default_rng(7000 + i).integers(0, 256, (h, w, c), dtype=np.uint8)
+        blob[f"lb_{i}_img"] = img
+        blob[f"lb_{i}_net"] = np.array([nw, nh], np.int32)
+        blob[f"lb_{i}_out"] = r16.letterbox_u8(img, nw, nh)
+    np.savez_compressed(os.path.join(OUT, "letterbox.npz"), **blob)
+    print("letterbox.npz", os.path.getsize(os.path.join(OUT, "letterbox.npz")) >> 10, "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "letterbox":
+        gen_letterbox()
+    else:
+        main()
+        gen_letterbox()

@@ -73,6 +73,15 @@ class Oracle:
         self.lib.orc_round_shift.restype = C.c_int64
         self.lib.orc_round_shift.argtypes = [C.c_int64, C.c_int]
 
+    def letterbox_u8(self, img, net_w, net_h):
+        """img: uint8 [h][w][c] (stb layout) -> float32 [c][net_h][net_w]"""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        ih, iw, ic = img.shape
+        out = np.empty((ic, net_h, net_w), np.float32)
+        rc = self.lib.orc_letterbox_u8(_vp(img), iw, ih, ic, _vp(out), net_w, net_h)
+        assert rc == 0, rc
+        return out
+
     def round_shift(self, v, s):
         return int(self.lib.orc_round_shift(int(v), int(s)))
 
@@ -190,6 +199,13 @@ class Ref:
             raise FileNotFoundError(REF_SO[precision] + " (run `make -C oracle ref` where /root/reference exists)")
         self.lib = C.CDLL(REF_SO[precision])
         assert self.lib.ref_precision_bits() == (16 if precision == "int16" else 32)
+
+    def letterbox_u8(self, img, net_w, net_h):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        ih, iw, ic = img.shape
+        out = np.empty((ic, net_h, net_w), np.float32)
+        assert self.lib.ref_letterbox_u8(_vp(img), iw, ih, ic, _vp(out), net_w, net_h) == 0
+        return out
 
     def yolo2_fpga(self, Input, Output, Weight, Beta, IFM_num, OFM_num, Ksize, Kstride, Input_w, Input_h, Output_w,
                    Output_h, Padding, IsNL, IsBN, TM, TN, TR, TC, OFM_num_bound, mLoopsxTM, mLoops_a1xTM, LayerType,

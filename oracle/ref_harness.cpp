@@ -7,6 +7,7 @@
 //
 //   ref_yolo2_fpga      -> YOLO2_FPGA            hls/models/yolov2/yolo2_accel.cpp:25-171
 //   ref_region_forward  -> forward_region_layer  src/core/yolo_region.cpp:123-141
+//   ref_letterbox_u8    -> letterbox_image       src/core/yolo_image.cpp:146-165 (+ the u8->float loop of :178-187)
 //   ref_full_forward    -> load_network + yolov2_hls_ps + get_network_boxes + do_nms_sort
 //                          (the call sequence of src/models/yolov2/yolov2_main.cpp:255-325)
 #include <cstdint>
@@ -140,6 +141,21 @@ int ref_region_boxes_nms(const float *region, int lw, int lh, int n, int classes
     }
     free_detections(dets, nboxes);
     return nboxes;
+}
+
+// The reference's own letterbox_image / resize_image (src/core/yolo_image.cpp:84-165) on an in-memory stb-layout image.
+// Only the u8 -> float loop of load_image_stb (:178-187, it reads a file) is repeated here to build the `image`.
+int ref_letterbox_u8(const unsigned char *hwc, int iw, int ih, int ic, float *out, int net_w, int net_h)
+{
+    image im = make_image(iw, ih, ic);
+    for (int k = 0; k < ic; ++k)
+        for (int j = 0; j < ih; ++j)
+            for (int i = 0; i < iw; ++i) im.data[i + iw * j + iw * ih * k] = (float)hwc[k + ic * i + ic * iw * j] / 255.;
+    image boxed = letterbox_image(im, net_w, net_h);
+    memcpy(out, boxed.data, sizeof(float) * (size_t)net_w * net_h * ic);
+    free_image(im);
+    free_image(boxed);
+    return 0;
 }
 
 } // extern "C"

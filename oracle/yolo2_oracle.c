@@ -624,3 +624,54 @@ int orc_net_forward_f32(const orc_layer *layers, int n_layers, const float *fram
     free(buf); free(input);
     return rc;
 }
+
+/* ---- image front-end ---------------------------------------------------------------------------
+ * load_image_stb's u8 -> float conversion (src/core/yolo_image.cpp:178-187), resize_image (:84-127:
+ * the two-pass bilinear, `part` along x first, then along y with set_pixel + add_pixel) and
+ * letterbox_image / fill_image / embed_image (:129-165).  Plain float arithmetic, one rounding per
+ * operation (built without -march like the reference, so no FMA contraction). */
+int orc_letterbox_u8(const unsigned char *hwc, int iw, int ih, int ic, float *out, int net_w, int net_h)
+{
+    if (!hwc || !out || iw <= 0 || ih <= 0 || ic <= 0 || net_w <= 0 || net_h <= 0) return -1;
+    int new_w, new_h;
+    if (((float)net_w / iw) < ((float)net_h / ih)) { new_w = net_w; new_h = (ih * net_w) / iw; }
+    else { new_h = net_h; new_w = (iw * net_h) / ih; }
+    float *im = (float *)malloc(sizeof(float) * (size_t)iw * ih * ic);
+    float *part = (float *)malloc(sizeof(float) * (size_t)new_w * ih * ic);
+    float *res = (float *)malloc(sizeof(float) * (size_t)new_w * new_h * ic);
+    if (!im || !part || !res) { free(im); free(part); free(res); return -2; }
+    for (int k = 0; k < ic; ++k)
+        for (int j = 0; j < ih; ++j)
+            for (int i = 0; i < iw; ++i) im[i + iw * j + iw * ih * k] = (float)hwc[k + ic * i + ic * iw * j] / 255.;
+    const float w_scale = (float)(iw - 1) / (new_w - 1);
+    const float h_scale = (float)(ih - 1) / (new_h - 1);
+    for (int k = 0; k < ic; ++k)
+        for (int r = 0; r < ih; ++r)
+            for (int c = 0; c < new_w; ++c) {
+                float val;
+                if (c == new_w - 1 || iw == 1) val = im[(iw - 1) + iw * r + iw * ih * k];
+                else {
+                    float sx = c * w_scale;
+                    int ix = (int)sx;
+                    float dx = sx - ix;
+                    val = (1 - dx) * im[ix + iw * r + iw * ih * k] + dx * im[ix + 1 + iw * r + iw * ih * k];
+                }
+                part[c + new_w * r + new_w * ih * k] = val;
+            }
+    for (int k = 0; k < ic; ++k)
+        for (int r = 0; r < new_h; ++r) {
+            float sy = r * h_scale;
+            int iy = (int)sy;
+            float dy = sy - iy;
+            for (int c = 0; c < new_w; ++c) res[c + new_w * r + new_w * new_h * k] = (1 - dy) * part[c + new_w * iy + new_w * ih * k];
+            if (r == new_h - 1 || ih == 1) continue;
+            for (int c = 0; c < new_w; ++c) res[c + new_w * r + new_w * new_h * k] += dy * part[c + new_w * (iy + 1) + new_w * ih * k];
+        }
+    for (size_t i = 0; i < (size_t)net_w * net_h * ic; ++i) out[i] = .5;
+    const int ox = (net_w - new_w) / 2, oy = (net_h - new_h) / 2;
+    for (int k = 0; k < ic; ++k)
+        for (int y = 0; y < new_h; ++y)
+            for (int x = 0; x < new_w; ++x) out[(ox + x) + net_w * (oy + y) + net_w * net_h * k] = res[x + new_w * y + new_w * new_h * k];
+    free(im); free(part); free(res);
+    return 0;
+}

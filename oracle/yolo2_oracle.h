@@ -108,6 +108,9 @@ int orc_net_forward_i16(const orc_layer *layers, int n_layers, const float *fram
 int orc_net_forward_f32(const orc_layer *layers, int n_layers, const float *frame,
                         const float *w_reorg, const float *bias, float **dump, float *region_out);
 
+/* stb u8 [ih][iw][ic] image -> float [ic][net_h][net_w] letterboxed network input (yolo_image.cpp:84-165,178-187) */
+int orc_letterbox_u8(const unsigned char *hwc, int iw, int ih, int ic, float *out, int net_w, int net_h);
+
 #ifdef __cplusplus
 }
 #endif

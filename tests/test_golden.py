@@ -81,3 +81,13 @@ def test_full_coco416_region_golden(tag, table, seed, full, oracle):
         pytest.skip("numpy RNG stream differs from the one the golden was generated with")
     region, _ = oracle.net_forward(net, frame, pack)
     assert np.array_equal(region.reshape(-1).view(np.uint32), full[f"{tag}_region"].view(np.uint32))
+
+
+# ---- image front-end: oracle vs the reference's letterbox_image frozen in letterbox.npz ----
+
+@pytest.mark.parametrize("i", range(7))
+def test_letterbox_golden(i, oracle):
+    g = np.load(os.path.join(GOLD, "letterbox.npz"))
+    nw, nh = (int(v) for v in g[f"lb_{i}_net"])
+    got = oracle.letterbox_u8(g[f"lb_{i}_img"], nw, nh)
+    assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), g[f"lb_{i}_out"].view(np.uint32))

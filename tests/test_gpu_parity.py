@@ -1,5 +1,7 @@
 """GPU parity tests: the CUDA path, called through the C ABI, against the oracle on the same
 seeded inputs.  Bar: bit-exact for int16; 1e-4 relative (of the layer's max |value|) for fp32."""
+import os
+
 import numpy as np
 import pytest
 
@@ -374,3 +376,42 @@ def test_tensor_core_net_bit_exact(tc, monkeypatch, oracle):
     net, pack = _net_case(416, 416, 3, 8, "stress", seed=11)
     frames = yw.synth_frames(net, 3, seed=2000)
     _check_net(net, pack, frames, oracle, max_batch=2)
+
+
+# ---- image front-end on the GPU ---------------------------------------------------------------------
+
+@pytest.mark.parametrize("i", range(7))
+def test_letterbox_golden_gpu(i, accel16):
+    """letterbox_kernel (csrc/bw_ops.cu) against the reference's letterbox_image output frozen in tests/golden/letterbox.npz."""
+    import torch
+    from yolo2_b200.accel import letterbox_image
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "letterbox.npz"))
+    nw, nh = (int(v) for v in g[f"lb_{i}_net"])
+    img = torch.from_numpy(g[f"lb_{i}_img"][None].copy()).cuda()
+    got = letterbox_image(accel16, img, nw, nh).cpu().numpy()[0]
+    assert np.array_equal(got.view(np.uint32), g[f"lb_{i}_out"].view(np.uint32))
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (333, 500), (1280, 720)])
+def test_letterbox_batch_vs_oracle(w, h, accel16, oracle):
+    """a batch of video-sized frames: every float of the 416x416 network input identical to the oracle's"""
+    import torch
+    from yolo2_b200.accel import letterbox_image
+    imgs = np.random.default_rng(w + h).integers(0, 256, (3, h, w, 3), dtype=np.uint8)
+    got = letterbox_image(accel16, torch.from_numpy(imgs).cuda(), 416, 416).cpu().numpy()
+    for f in range(3):
+        assert np.array_equal(got[f].view(np.uint32), oracle.letterbox_u8(imgs[f], 416, 416).view(np.uint32))
+
+
+def test_forward_images_equals_forward_of_letterboxed(oracle):
+    """yolo2cuda_net_forward_images_host == letterbox (oracle) + yolo2cuda_net_forward_host, bit for bit, across passes"""
+    net, pack = _net_case(416, 416, 3, 8, "default", seed=5)
+    imgs = np.random.default_rng(99).integers(0, 256, (3, 120, 160, 3), dtype=np.uint8)
+    y = Yolo2Net(net, pack, max_batch=2)
+    try:
+        frames = np.stack([oracle.letterbox_u8(im, 416, 416) for im in imgs])
+        want = y.forward(frames)
+        got = y.forward_images(imgs)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    finally:
+        y.close()

@@ -108,3 +108,10 @@ def test_generalised_driver_vs_real_yolo2_fpga(width, classes, table, precision,
         assert np.array_equal(got_region.view(np.uint32), want_region.view(np.uint32))
     else:
         assert np.abs(got_region - want_region).max() <= 1e-5
+
+
+@pytest.mark.parametrize("w,h,c,nw,nh", [(640, 480, 3, 416, 416), (333, 500, 3, 416, 416), (416, 416, 3, 416, 416), (77, 31, 1, 40, 56)])
+def test_letterbox_oracle_vs_reference(w, h, c, nw, nh, oracle, ref16):
+    """orc_letterbox_u8 against the reference's own letterbox_image (yolo_image.cpp:146-165), bit for bit."""
+    img = np.random.default_rng(w * 1000 + h).integers(0, 256, (h, w, c), dtype=np.uint8)
+    assert np.array_equal(oracle.letterbox_u8(img, nw, nh).view(np.uint32), ref16.letterbox_u8(img, nw, nh).view(np.uint32))

@@ -407,4 +407,71 @@ void launch_region(const void *in, float *out, int B, int w, int h, int n, int c
     }
 }
 
+// ---- image front-end: stb u8 HWC image -> float CHW in [0,1] -> letterbox (bilinear resize + 0.5 fill) -------------------
+// Bit-exact restatement of load_image_stb's conversion (src/core/yolo_image.cpp:178-187), resize_image (:84-127, the darknet
+// two-pass bilinear: first along x into `part`, then along y) and letterbox_image / embed_image (:129-165).  Every float
+// operation of the reference is one rounded operation here (__fmul_rn / __fadd_rn / __fsub_rn: no FMA contraction; the
+// reference is built without -march, so g++ emits separate mulss/addss).  One thread = one pixel of the network input.
+struct LetterboxParams {
+    int iw, ih, ic, net_w, net_h, new_w, new_h, off_x, off_y;
+    float w_scale, h_scale;
+};
+
+__device__ __forceinline__ float lb_src(const unsigned char *img, const LetterboxParams &p, int x, int y, int k)
+{
+    return __double2float_rn((double)img[k + p.ic * x + p.ic * p.iw * y] / 255.);   // (float)data[src_index]/255.
+}
+// one pixel of resize_image's first pass: part(cx, r, k)
+__device__ __forceinline__ float lb_part(const unsigned char *img, const LetterboxParams &p, int cx, int r, int k)
+{
+    if (cx == p.new_w - 1 || p.iw == 1) return lb_src(img, p, p.iw - 1, r, k);
+    const float sx = __fmul_rn((float)cx, p.w_scale);
+    const int ix = (int)sx;
+    const float dx = __fsub_rn(sx, (float)ix);
+    return __fadd_rn(__fmul_rn(__fsub_rn(1.0f, dx), lb_src(img, p, ix, r, k)), __fmul_rn(dx, lb_src(img, p, ix + 1, r, k)));
+}
+
+__global__ void letterbox_kernel(const unsigned char *__restrict__ src, float *__restrict__ dst, int B, const LetterboxParams p)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)p.net_w * p.net_h;
+    if (idx >= per * B) return;
+    const int f = (int)(idx / per);
+    const int rem = (int)(idx - (long long)f * per);
+    const int y = rem / p.net_w, x = rem - y * p.net_w;
+    const unsigned char *img = src + (size_t)f * p.iw * p.ih * p.ic;
+    float *out = dst + (size_t)f * p.ic * per;
+    const int cx = x - p.off_x, r = y - p.off_y;
+    const bool inside = cx >= 0 && cx < p.new_w && r >= 0 && r < p.new_h;
+    float sy = 0.f, dy = 0.f;
+    int iy = 0;
+    if (inside) {
+        sy = __fmul_rn((float)r, p.h_scale);
+        iy = (int)sy;
+        dy = __fsub_rn(sy, (float)iy);
+    }
+    for (int k = 0; k < p.ic; ++k) {
+        float v = 0.5f;                                                       // fill_image(boxed, .5)
+        if (inside) {
+            v = __fmul_rn(__fsub_rn(1.0f, dy), lb_part(img, p, cx, iy, k));   // set_pixel(resized, ..., (1-dy) * part(iy))
+            if (!(r == p.new_h - 1 || p.ih == 1)) v = __fadd_rn(v, __fmul_rn(dy, lb_part(img, p, cx, iy + 1, k)));   // add_pixel
+        }
+        out[(size_t)k * per + rem] = v;
+    }
+}
+
+void launch_letterbox(const unsigned char *src, float *dst, int B, int iw, int ih, int ic, int net_w, int net_h, cudaStream_t st)
+{
+    LetterboxParams p;
+    p.iw = iw; p.ih = ih; p.ic = ic; p.net_w = net_w; p.net_h = net_h;
+    if (((float)net_w / iw) < ((float)net_h / ih)) { p.new_w = net_w; p.new_h = (ih * net_w) / iw; }   // letterbox_image :150-156
+    else { p.new_h = net_h; p.new_w = (iw * net_h) / ih; }
+    p.w_scale = (float)(iw - 1) / (p.new_w - 1);     // resize_image :89-90 (host float division, same expression)
+    p.h_scale = (float)(ih - 1) / (p.new_h - 1);
+    p.off_x = (net_w - p.new_w) / 2;
+    p.off_y = (net_h - p.new_h) / 2;
+    const long long total = (long long)B * net_w * net_h;
+    letterbox_kernel<<<blocks_for(total, 256), 256, 0, st>>>(src, dst, B, p);
+}
+
 }  // namespace y2

@@ -380,6 +380,8 @@ struct yolo2cuda_net {
     void *d_frames = nullptr;      // staging for forward_host: float [max_batch][c][h][w]
     void *d_region = nullptr;      // staging for forward_host
     void *d_frames2[2] = {nullptr, nullptr}, *d_region2[2] = {nullptr, nullptr};   // double-buffered staging
+    void *d_lb_frames = nullptr, *d_lb_region = nullptr, *d_lb_img = nullptr;       // forward_images_host: letterboxed frames, region, raw u8 images
+    size_t lb_img_bytes = 0;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     void *d_wblob = nullptr, *d_bblob = nullptr;
@@ -658,6 +660,7 @@ int yolo2cuda_net_destroy(yolo2cuda_net *net)
     cudaSetDevice(net->ctx->device);
     cudaStreamSynchronize(net->ctx->stream);
     for (void *p : net->owned) cudaFree(p);
+    if (net->d_lb_img) cudaFree(net->d_lb_img);
     for (auto ev : net->ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
         if (net->ev_h2d[i]) cudaEventDestroy(net->ev_h2d[i]);
@@ -832,6 +835,50 @@ int yolo2cuda_net_forward_host(yolo2cuda_net *net, const float *frames, int batc
         CUDA_OK(ctx, cudaEventRecord(net->ev_d2h[buf], net->s_d2h));
     }
     CUDA_OK(ctx, cudaStreamSynchronize(net->s_d2h));
+    CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_letterbox_dev(yolo2cuda_ctx *ctx, const unsigned char *src, int batch, int iw, int ih, int ic, float *dst,
+                            int net_w, int net_h)
+{
+    if (!ctx || !src || !dst) return YOLO2CUDA_ERROR;
+    if (batch <= 0 || iw <= 0 || ih <= 0 || ic <= 0 || net_w <= 0 || net_h <= 0) return fail(ctx, YOLO2CUDA_ERROR, "letterbox: bad dimensions");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    launch_letterbox(src, dst, batch, iw, ih, ic, net_w, net_h, ctx->stream);
+    ctx->launches += 1;
+    CUDA_OK(ctx, cudaGetLastError());
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_net_forward_images_host(yolo2cuda_net *net, const unsigned char *images, int batch, int iw, int ih, float *region_out)
+{
+    if (!net || !images || !region_out || batch <= 0 || iw <= 0 || ih <= 0) return YOLO2CUDA_ERROR;
+    yolo2cuda_ctx *ctx = net->ctx;
+    if (!net->weights_loaded) return fail(ctx, YOLO2CUDA_ERROR, "weights not loaded");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t frame_elems = (size_t)net->in_c * net->in_h * net->in_w, img_bytes = (size_t)iw * ih * net->in_c;
+    int rc;
+    if (!net->d_lb_frames) {
+        if ((rc = net_alloc(net, &net->d_lb_frames, frame_elems * net->max_batch * sizeof(float)))) return rc;
+        if ((rc = net_alloc(net, &net->d_lb_region, net->region_outputs * net->max_batch * sizeof(float)))) return rc;
+    }
+    if (net->lb_img_bytes < img_bytes * net->max_batch) {
+        if (net->d_lb_img) cudaFree(net->d_lb_img);
+        net->d_lb_img = nullptr;
+        CUDA_OK(ctx, cudaMalloc(&net->d_lb_img, img_bytes * net->max_batch));
+        net->lb_img_bytes = img_bytes * net->max_batch;
+    }
+    for (int b0 = 0; b0 < batch; b0 += net->max_batch) {
+        const int B = batch - b0 < net->max_batch ? batch - b0 : net->max_batch;
+        CUDA_OK(ctx, cudaMemcpyAsync(net->d_lb_img, images + (size_t)b0 * img_bytes, img_bytes * B, cudaMemcpyHostToDevice, st));
+        launch_letterbox((const unsigned char *)net->d_lb_img, (float *)net->d_lb_frames, B, iw, ih, net->in_c, net->in_w, net->in_h, st);
+        ctx->launches += 1;
+        if ((rc = forward_chunk(net, (const float *)net->d_lb_frames, B, (float *)net->d_lb_region))) return rc;
+        CUDA_OK(ctx, cudaMemcpyAsync(region_out + (size_t)b0 * net->region_outputs, net->d_lb_region, net->region_outputs * B * sizeof(float),
+                                     cudaMemcpyDeviceToHost, st));
+    }
     CUDA_OK(ctx, cudaStreamSynchronize(st));
     return YOLO2CUDA_SUCCESS;
 }

@@ -53,6 +53,8 @@ SYMBOLS = {
                                              C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "yolo2cuda_net_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo2cuda_net_forward_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "yolo2cuda_letterbox_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "yolo2cuda_net_forward_images_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "yolo2cuda_net_get_layer_output": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "yolo2cuda_net_region_q": (C.c_int, [C.c_void_p]),
     "yolo2cuda_net_launches_per_forward": (C.c_uint64, [C.c_void_p]),

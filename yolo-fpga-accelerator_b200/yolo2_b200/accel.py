@@ -86,6 +86,18 @@ class Accelerator:
 Tn, Tm, Tr, Tc, OnChipIB = 4, 32, 13, 13, 27
 
 
+def letterbox_image(acc: "Accelerator", images, net_w: int, net_h: int):
+    """GPU image front-end (reference: load_image_stb + letterbox_image, src/core/yolo_image.cpp:84-187).
+    images: torch.uint8 CUDA tensor [batch][h][w][c] (stb layout) -> torch.float32 CUDA tensor [batch][c][net_h][net_w]."""
+    import torch
+    assert images.is_cuda and images.dtype == torch.uint8 and images.dim() == 4 and images.is_contiguous()
+    b, ih, iw, ic = images.shape
+    out = torch.empty((b, ic, net_h, net_w), dtype=torch.float32, device=images.device)
+    acc.set_stream(torch.cuda.current_stream(images.device).cuda_stream)
+    _capi.check(acc.ctx, acc.lib.yolo2cuda_letterbox_dev(acc.ctx, C.c_void_p(images.data_ptr()), b, iw, ih, ic, C.c_void_p(out.data_ptr()), net_w, net_h))
+    return out
+
+
 def conv_call_args(c, n, size, stride, w, h, pad, leaky, bn=0):
     ow = (w - size + 2 * pad) // stride + 1
     oh = (h - size + 2 * pad) // stride + 1

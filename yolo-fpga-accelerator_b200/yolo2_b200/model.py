@@ -67,6 +67,18 @@ class Yolo2Net:
         _capi.check(self.accel.ctx, rc)
         return self._shape_region(out, B)
 
+    def forward_images(self, images: np.ndarray) -> np.ndarray:
+        """Raw stb-layout images uint8 [batch][h][w][c] (all one size) -> letterbox on the GPU -> network.
+        Reference call sequence: load_image_stb, letterbox_image, yolov2_hls_ps (yolov2_main.cpp:255-292)."""
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        B, ih, iw, ic = images.shape
+        assert ic == self.net.c
+        out = np.empty((B, self.region_outputs), np.float32)
+        rc = self.lib.yolo2cuda_net_forward_images_host(self.handle, images.ctypes.data_as(C.c_void_p), B, iw, ih,
+                                                        out.ctypes.data_as(C.c_void_p))
+        _capi.check(self.accel.ctx, rc)
+        return self._shape_region(out, B)
+
     def forward_ptr(self, frames_ptr: int, batch: int, out_ptr: int, device: bool):
         """Raw-pointer form (torch tensors: .data_ptr()). device=True is asynchronous."""
         fn = self.lib.yolo2cuda_net_forward_dev if device else self.lib.yolo2cuda_net_forward_host
