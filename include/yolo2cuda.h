@@ -57,6 +57,11 @@ typedef struct yolo2cuda_net yolo2cuda_net;   /* one loaded network: plan, weigh
 int yolo2cuda_create(yolo2cuda_ctx **ctx, int device, int precision);
 int yolo2cuda_destroy(yolo2cuda_ctx *ctx);
 /* Launch all work of this context on `cuda_stream` (a cudaStream_t; NULL = the context's own). */
+/* Tile parameters of the reference BUILD this context emulates (scripts/hw_params_gen.py --tn/--tm ->
+ * hls/core/params.hpp): Tn = input-channel tile = the ROUNDING GROUP of the int16 accumulator
+ * (core_scheduler.cpp:45, core_compute.cpp:65-120), Tm = output-channel weight block.  Defaults 4 / 32 (the
+ * reference's); results are bit-exact to a reference compiled with the same values.  Set before net_create. */
+int yolo2cuda_set_tile_params(yolo2cuda_ctx *ctx, int Tn, int Tm);
 int yolo2cuda_set_stream(yolo2cuda_ctx *ctx, void *cuda_stream);
 int yolo2cuda_synchronize(yolo2cuda_ctx *ctx);
 /* Text of the last error on this context (never NULL). */

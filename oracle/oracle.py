@@ -39,8 +39,13 @@ def build(ref=True, quiet=True):
         subprocess.check_call(["make", "-C", HERE, "ref"], stdout=out)
 
 
-def have_ref(precision="int16"):
-    return os.path.exists(REF_SO[precision])
+def ref_so(precision="int16", tn=4):
+    """library of the reference BUILT with rounding group tn (oracle/Makefile: `make ref TN=<tn>` / `make ref-variants`)"""
+    return REF_SO[precision] if tn == 4 else REF_SO[precision].replace(".so", f"_tn{tn}.so")
+
+
+def have_ref(precision="int16", tn=4):
+    return os.path.exists(ref_so(precision, tn))
 
 
 def _vp(a):
@@ -81,6 +86,10 @@ class Oracle:
         rc = self.lib.orc_letterbox_u8(_vp(img), iw, ih, ic, _vp(out), net_w, net_h)
         assert rc == 0, rc
         return out
+
+    def set_tile_params(self, tn=4, tm=32):
+        """reference build parameters used by net_forward (conv() takes TM/TN per call)"""
+        self.lib.orc_set_tile_params(int(tn), int(tm))
 
     def round_shift(self, v, s):
         return int(self.lib.orc_round_shift(int(v), int(s)))
@@ -192,13 +201,17 @@ class Oracle:
 class Ref:
     """The real reference (compiled unmodified). precision: "int16" | "fp32"."""
 
-    def __init__(self, precision="int16"):
+    def __init__(self, precision="int16", tn=4):
         self.precision = precision
         self.dtype = np.int16 if precision == "int16" else np.float32
-        if not have_ref(precision):
-            raise FileNotFoundError(REF_SO[precision] + " (run `make -C oracle ref` where /root/reference exists)")
-        self.lib = C.CDLL(REF_SO[precision])
+        if not have_ref(precision, tn):
+            raise FileNotFoundError(ref_so(precision, tn) + " (run `make -C oracle ref [ref-variants]` where /root/reference exists)")
+        self.lib = C.CDLL(ref_so(precision, tn))
         assert self.lib.ref_precision_bits() == (16 if precision == "int16" else 32)
+        t = (C.c_int * 5)()
+        self.lib.ref_tile_params(C.byref(t, 0), C.byref(t, 4), C.byref(t, 8), C.byref(t, 12), C.byref(t, 16))
+        assert t[0] == tn, (t[0], tn)
+        self.tn, self.tm = t[0], t[1]
 
     def letterbox_u8(self, img, net_w, net_h):
         img = np.ascontiguousarray(img, dtype=np.uint8)

@@ -44,6 +44,11 @@ static inline size_t reorg_woff(int m, int c, int tap, int ifm, int ofm, int k2,
     return (size_t)m0 * ifm * k2 + (size_t)tmm * n0 * k2 + ((size_t)tap * tmm + (m - m0)) * tnn + (c - n0);
 }
 
+/* Tile parameters of the reference BUILD (scripts/hw_params_gen.py --tn/--tm -> hls/core/params.hpp): Tn is the rounding
+ * group of the int16 accumulator (core_scheduler.cpp:45), Tm the weight block.  Used by the net-level drivers below. */
+static int g_tn = 4, g_tm = 32;
+void orc_set_tile_params(int tn, int tm) { g_tn = tn > 0 ? tn : 4; g_tm = tm > 0 ? tm : 32; }
+
 int orc_conv_i16(const int16_t *in, int16_t *out, const int16_t *w_reorg, const int16_t *bias,
                  int ifm, int ofm, int ksize, int kstride, int iw, int ih, int ow, int oh,
                  int pad, int is_nl, int TM, int TN, int qw, int qa_in, int qa_out, int qb)
@@ -495,7 +500,7 @@ int orc_net_forward_i16(const orc_layer *layers, int n_layers, const float *fram
             buf[i] = (int16_t *)calloc(fm_elems(l->out_c, l->out_h, l->out_w) + 64, sizeof(int16_t));
         switch (l->type) {
         case ORC_CONV: {
-            int TM = ORC_MIN(l->n, 32), TN = ORC_MIN(l->c, 4); /* :307-308 */
+            int TM = ORC_MIN(l->n, g_tm), TN = ORC_MIN(l->c, g_tn); /* :307-308 */
             int qa_in = (conv_idx < n_act_q) ? act_q[conv_idx] : current_qa;         /* :314 */
             int qa_out = (conv_idx + 1 < n_act_q) ? act_q[conv_idx + 1] : qa_in;     /* :315 */
             if (pending_route_q >= 0) qa_in = pending_route_q;                       /* :318-320 */
@@ -576,7 +581,7 @@ int orc_net_forward_f32(const orc_layer *layers, int n_layers, const float *fram
             buf[i] = (float *)calloc(fm_elems(l->out_c, l->out_h, l->out_w) + 64, sizeof(float));
         switch (l->type) {
         case ORC_CONV: {
-            int TM = ORC_MIN(l->n, 32), TN = ORC_MIN(l->c, 4);
+            int TM = ORC_MIN(l->n, g_tm), TN = ORC_MIN(l->c, g_tn);
             rc = orc_conv_f32(src, buf[i], w_reorg + woff, bias + boff, l->c, l->n, l->size, l->stride,
                               l->w, l->h, l->out_w, l->out_h, l->pad, l->leaky, TM, TN);
             woff += (size_t)l->c * l->n * l->size * l->size;

@@ -111,6 +111,9 @@ int orc_net_forward_f32(const orc_layer *layers, int n_layers, const float *fram
 /* stb u8 [ih][iw][ic] image -> float [ic][net_h][net_w] letterboxed network input (yolo_image.cpp:84-165,178-187) */
 int orc_letterbox_u8(const unsigned char *hwc, int iw, int ih, int ic, float *out, int net_w, int net_h);
 
+/* reference build parameters Tn (rounding group) / Tm used by orc_net_forward_* (defaults 4 / 32) */
+void orc_set_tile_params(int tn, int tm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,10 +9,10 @@ def align8(w):
     return (w + 7) & ~7
 
 
-def make_conv_case(seed, c, n, size, stride, w, h, leaky, dtype=np.int16, amp=600, xamp=2000, pad=None, poison=12345):
+def make_conv_case(seed, c, n, size, stride, w, h, leaky, dtype=np.int16, amp=600, xamp=2000, pad=None, poison=12345, tn=4, tm=32):
     rng = np.random.default_rng(seed)
     pad = size // 2 if pad is None else pad
-    a = conv_call_args(c, n, size, stride, w, h, pad, leaky)
+    a = conv_call_args(c, n, size, stride, w, h, pad, leaky, tn=tn, tm=tm)
     x = np.full((c, h, align8(w)), poison, dtype)           # poisoned pad columns must not matter
     if dtype == np.int16:
         x[:, :, :w] = rng.integers(-xamp, xamp + 1, (c, h, w))

@@ -415,3 +415,25 @@ def test_forward_images_equals_forward_of_letterboxed(oracle):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     finally:
         y.close()
+
+
+# ---- rounding-group variants: yolo2cuda_set_tile_params emulates a reference built with another Tn ----
+
+@pytest.mark.parametrize("tn", [8, 16, 32])
+def test_tile_param_variants_bit_exact(tn, oracle):
+    from yolo2_b200.accel import Accelerator
+    acc = Accelerator(0, "int16")
+    try:
+        acc.set_tile_params(tn, 32)
+        for i, (c, n, k, w, h, q, amp) in enumerate([(64, 40, 3, 13, 13, (14, 10, 10, 10), 600), (37, 33, 3, 20, 11, (13, 9, 12, 7), 32767),
+                                                     (96, 64, 1, 19, 19, (12, 12, 7, 8), 3000), (3, 16, 3, 26, 26, (14, 10, 10, 10), 600)]):
+            a, x, wr, b, _ = make_conv_case(900 + 10 * tn + i, c, n, k, 1, w, h, 1, amp=amp, xamp=32767 if amp > 600 else 2000, tn=tn)
+            want = oracle_conv(oracle, a, x, wr, b, q)
+            got = accel_call(acc, a, x, wr, b, q)
+            assert np.array_equal(valid(got, w), valid(want, w)), (tn, c, n, k, acc.last_kernel)
+        # a TN the emulated build does not have is the reference's assert (yolo2_accel.cpp:75-87)
+        a, x, wr, b, _ = make_conv_case(1, 64, 32, 3, 1, 13, 13, 1, tn=2 * tn)
+        with pytest.raises(Exception):
+            accel_call(acc, a, x, wr, b, (14, 10, 10, 10))
+    finally:
+        acc.close()

@@ -115,3 +115,21 @@ def test_letterbox_oracle_vs_reference(w, h, c, nw, nh, oracle, ref16):
     """orc_letterbox_u8 against the reference's own letterbox_image (yolo_image.cpp:146-165), bit for bit."""
     img = np.random.default_rng(w * 1000 + h).integers(0, 256, (h, w, c), dtype=np.uint8)
     assert np.array_equal(oracle.letterbox_u8(img, nw, nh).view(np.uint32), ref16.letterbox_u8(img, nw, nh).view(np.uint32))
+
+
+# ---- rounding-group variants (SURVEY.md 8f-4): the reference BUILT with --tn 8/16/32 (oracle/Makefile ref-variants) ----
+
+@pytest.mark.parametrize("tn", [8, 16, 32])
+def test_conv_int16_variant_builds(tn, oracle):
+    """orc_conv_i16 with TN = tn against the unmodified YOLO2_FPGA of a reference compiled with Tn = tn, bit for bit"""
+    from oracle.oracle import Ref, have_ref
+    if not have_ref("int16", tn):
+        pytest.skip(f"oracle/_ref/libref_int16_tn{tn}.so not built (make -C oracle ref-variants)")
+    ref = Ref("int16", tn)
+    for i, (c, n, k, w, h, q, amp) in enumerate([(64, 40, 3, 13, 13, (14, 10, 10, 10), 600), (37, 33, 3, 20, 11, (13, 9, 12, 7), 32767),
+                                                 (96, 64, 1, 19, 19, (12, 12, 7, 8), 3000), (3, 16, 3, 26, 26, (14, 10, 10, 10), 600)]):
+        a, x, wr, b, _ = make_conv_case(900 + 10 * tn + i, c, n, k, 1, w, h, 1, amp=amp, xamp=32767 if amp > 600 else 2000, tn=tn)
+        assert a["TN"] == min(c, tn)
+        want = ref.run_layer(x, wr, b, a, q)
+        got = oracle_conv(oracle, a, x, wr, b, q)
+        assert np.array_equal(valid(got, w), valid(want, w))

@@ -25,6 +25,7 @@ struct yolo2cuda_ctx {
     uint64_t launches = 0;
     const char *last_kernel = "";
     int force_generic = 0;
+    int Tn = YOLO2CUDA_Tn, Tm = YOLO2CUDA_Tm;   // tile parameters of the emulated reference build (yolo2cuda_set_tile_params)
     int use_tc = 0;   // YOLO2CUDA_TC=1: tcgen05 conv (csrc/conv_i16_tc.cu) where eligible
     int tc_min_ofm = 96;
     // growable device scratch for the per-layer entry points
@@ -75,7 +76,8 @@ size_t c4_elems(int c, int h, int w) { return (size_t)ceil_div(c, 4) * h * w * 4
 // The checks of yolo2_accel.cpp:75-87 (and the board driver's validate_conv_params,
 // linux_app/src/yolo2_accel_linux.c:383-414), returned as an error instead of assert().
 const char *validate_layer_args(int IFM, int OFM, int K, int S, int Iw, int Ih, int Ow, int Oh, int Pad, int TM, int TN,
-                                int TR, int TC, int bound, int mLxTM, int mLa1xTM, int type)
+                                int TR, int TC, int bound, int mLxTM, int mLa1xTM, int type, int Tn_build = YOLO2CUDA_Tn,
+                                int Tm_build = YOLO2CUDA_Tm)
 {
     if (OFM <= 0 || OFM > 2048) return "OFM_num out of (0,2048]";
     if (IFM <= 0 || IFM > 2048) return "IFM_num out of (0,2048]";
@@ -84,8 +86,8 @@ const char *validate_layer_args(int IFM, int OFM, int K, int S, int Iw, int Ih, 
     if (Iw <= 0 || Iw > 1024 || Ih <= 0 || Ih > 1024) return "input dims out of (0,1024]";
     if (Ow <= 0 || Ow > 1024 || Oh <= 0 || Oh > 1024) return "output dims out of (0,1024]";
     if (Pad < 0 || Pad > 4) return "Padding out of [0,4]";
-    if (TM <= 0 || TM > YOLO2CUDA_Tm) return "TM out of (0,Tm]";
-    if (TN < 0 || TN > YOLO2CUDA_Tn) return "TN out of [0,Tn]";
+    if (TM <= 0 || TM > Tm_build) return "TM out of (0,Tm]";
+    if (TN < 0 || TN > Tn_build) return "TN out of [0,Tn]";
     if (TR <= 0 || TR > YOLO2CUDA_Tr) return "TR out of (0,Tr]";
     if (TC <= 0 || TC > YOLO2CUDA_Tc) return "TC out of (0,Tc]";
     if (type < 0 || type > 2) return "LayerType must be 0, 1 or 2";
@@ -112,7 +114,7 @@ int run_conv_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, cons
     cudaStream_t st = ctx->stream;
     const int so = Qa_in + Qw - Qa_out, sb = Qb - Qa_out;
     bool fast = !ctx->force_generic && (K == 1 || K == 3) && S == 1 && Pad == K / 2 && Ow == Iw && Oh == Ih &&
-                (TN == 4 || IFM <= TN);
+                (TN == 4 || (IFM <= TN && IFM <= 4));   // the C4 kernels' rounding group is 4 channels (or all of them when IFM <= 4)
     if (ctx->elem == 2) fast = fast && fast_shift_ok(so);
     ConvFastParams p{};
     if (fast) {
@@ -215,6 +217,15 @@ int yolo2cuda_destroy(yolo2cuda_ctx *ctx)
     return YOLO2CUDA_SUCCESS;
 }
 
+int yolo2cuda_set_tile_params(yolo2cuda_ctx *ctx, int Tn, int Tm)
+{
+    if (!ctx) return YOLO2CUDA_ERROR;
+    if (Tn <= 0 || Tn > 64 || Tm <= 0 || Tm > 2048) return fail(ctx, YOLO2CUDA_ERROR, "tile parameters out of range (0 < Tn <= 64, 0 < Tm <= 2048)");
+    ctx->Tn = Tn;
+    ctx->Tm = Tm;
+    return YOLO2CUDA_SUCCESS;
+}
+
 int yolo2cuda_set_stream(yolo2cuda_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) return YOLO2CUDA_ERROR;
@@ -243,7 +254,7 @@ int yolo2cuda_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, con
     if (!ctx) return YOLO2CUDA_ERROR;
     if (!Input || !Output) return fail(ctx, YOLO2CUDA_ERROR, "Input/Output must not be NULL");
     const char *why = validate_layer_args(IFM_num, OFM_num, Ksize, Kstride, Input_w, Input_h, Output_w, Output_h, Padding,
-                                          TM, TN, TR, TC, OFM_num_bound, mLoopsxTM, mLoops_a1xTM, LayerType);
+                                          TM, TN, TR, TC, OFM_num_bound, mLoopsxTM, mLoops_a1xTM, LayerType, ctx->Tn, ctx->Tm);
     if (why) return fail(ctx, YOLO2CUDA_ERROR, "invalid layer arguments: %s", why);
     CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -276,7 +287,7 @@ int yolo2cuda_layer_host(yolo2cuda_ctx *ctx, const void *Input, void *Output, co
     if (!ctx) return YOLO2CUDA_ERROR;
     if (!Input || !Output) return fail(ctx, YOLO2CUDA_ERROR, "Input/Output must not be NULL");
     const char *why = validate_layer_args(IFM_num, OFM_num, Ksize, Kstride, Input_w, Input_h, Output_w, Output_h, Padding,
-                                          TM, TN, TR, TC, OFM_num_bound, mLoopsxTM, mLoops_a1xTM, LayerType);
+                                          TM, TN, TR, TC, OFM_num_bound, mLoopsxTM, mLoops_a1xTM, LayerType, ctx->Tn, ctx->Tm);
     if (why) return fail(ctx, YOLO2CUDA_ERROR, "invalid layer arguments: %s", why);
     CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -452,7 +463,7 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
                 ctx->last_kernel = l.variant;
             } else {
                 // contract-complete fallback, one frame at a time through the planar kernels
-                const int TM = l.d.n < 32 ? l.d.n : 32, TN = l.d.c < 4 ? l.d.c : 4;
+                const int TM = l.d.n < ctx->Tm ? l.d.n : ctx->Tm, TN = l.d.c < ctx->Tn ? l.d.c : ctx->Tn;
                 for (int f = 0; f < B; ++f) {
                     launch_c4_to_planar((char *)l.in.base + (size_t)f * l.in.frame_stride * e, net->d_tmp_planar_in, 1, l.d.c,
                                         l.d.h, l.d.w, 0, 0, e, st);
@@ -722,9 +733,10 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                 pending_route_q = -1;
             }
             const int so = l.Qa_in + l.Qw - l.Qa_out;
-            const int TM = l.d.n < 32 ? l.d.n : 32, TN = l.d.c < 4 ? l.d.c : 4;  // yolo2_model.cpp:307-308
+            const int TM = l.d.n < ctx->Tm ? l.d.n : ctx->Tm, TN = l.d.c < ctx->Tn ? l.d.c : ctx->Tn;  // yolo2_model.cpp:307-308
             l.fast = !ctx->force_generic && (l.d.size == 1 || l.d.size == 3) && l.d.stride == 1 && l.d.pad == l.d.size / 2 &&
-                     l.d.out_w == l.d.w && l.d.out_h == l.d.h && (e == 4 || fast_shift_ok(so));
+                     l.d.out_w == l.d.w && l.d.out_h == l.d.h && (e == 4 || fast_shift_ok(so)) &&
+                     (e == 4 || TN == 4 || l.d.c <= 4);   // int16: the C4 kernels' rounding group is 4 channels
             if (l.fast) {
                 ConvFastParams p{};
                 p.B = net->max_batch; p.H = l.d.h; p.W = l.d.w; p.G = ceil_div(l.d.c, 4); p.OFM = l.d.n;

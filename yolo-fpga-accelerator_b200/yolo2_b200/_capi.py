@@ -37,6 +37,7 @@ _LAYER_ARGS = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.
 SYMBOLS = {
     "yolo2cuda_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "yolo2cuda_destroy": (C.c_int, [C.c_void_p]),
+    "yolo2cuda_set_tile_params": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "yolo2cuda_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "yolo2cuda_synchronize": (C.c_int, [C.c_void_p]),
     "yolo2cuda_last_error": (C.c_char_p, [C.c_void_p]),

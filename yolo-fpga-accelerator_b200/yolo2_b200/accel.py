@@ -35,6 +35,11 @@ class Accelerator:
         except Exception:
             pass
 
+    def set_tile_params(self, tn: int = 4, tm: int = 32):
+        """Emulate a reference BUILT with another rounding group Tn / weight block Tm (scripts/hw_params_gen.py --tn/--tm)."""
+        _capi.check(self.ctx, self.lib.yolo2cuda_set_tile_params(self.ctx, tn, tm))
+        self.tn, self.tm = tn, tm
+
     def set_stream(self, cuda_stream_ptr):
         _capi.check(self.ctx, self.lib.yolo2cuda_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr)))
 
@@ -98,12 +103,13 @@ def letterbox_image(acc: "Accelerator", images, net_w: int, net_h: int):
     return out
 
 
-def conv_call_args(c, n, size, stride, w, h, pad, leaky, bn=0):
+def conv_call_args(c, n, size, stride, w, h, pad, leaky, bn=0, tn=Tn, tm=Tm):
+    """tn / tm: the reference build's tile parameters (scripts/hw_params_gen.py --tn/--tm); defaults are its defaults"""
     ow = (w - size + 2 * pad) // stride + 1
     oh = (h - size + 2 * pad) // stride + 1
     TR = min((OnChipIB - size) // stride + 1, Tr, oh)
     TC = min((OnChipIB - size) // stride + 1, Tc, ow)
-    TM, TN = min(n, Tm), min(c, Tn)
+    TM, TN = min(n, tm), min(c, tn)
     mLoops = math.ceil(n / TM)
     return dict(IFM_num=c, OFM_num=n, Ksize=size, Kstride=stride, Input_w=w, Input_h=h, Output_w=ow, Output_h=oh,
                 Padding=pad, IsNL=leaky, IsBN=bn, TM=TM, TN=TN, TR=TR, TC=TC, OFM_num_bound=(mLoops + 1) * TM,

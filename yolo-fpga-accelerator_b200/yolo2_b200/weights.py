@@ -113,7 +113,7 @@ def save_reference_files(pack: WeightsPack, net: _cfg.Network, directory: str):
 
 
 def synth_pack(net: _cfg.Network, precision: str = "int16", seed: int = 0, table: str = "default",
-               w_amp: int = 600, b_amp: int = 2000) -> WeightsPack:
+               w_amp: int = 600, b_amp: int = 2000, tn: int = Tn, tm: int = Tm) -> WeightsPack:
     """Seeded synthetic weights in darknet order, reorganised like yolov2_weight_gen does.
     table: "default" (Qw=14,Qb=10,Qa=10 everywhere), "stress" (per-layer random Qa in [7,12],
     Qw in [12,15], Qb in [8,12]: both shift signs and the route Q-align), "saturate" (full-range
@@ -130,7 +130,7 @@ def synth_pack(net: _cfg.Network, precision: str = "int16", seed: int = 0, table
             amp = 32767 if table == "saturate" else w_amp
             w = rng.integers(-amp, amp + 1, size=(l.n, l.c, k2)).astype(np.int16)
             b = rng.integers(-b_amp, b_amp + 1, size=l.n).astype(np.int16)
-        ws.append(weight_reorg(w, l.c, l.n, l.size, min(l.n, Tm), min(l.c, Tn)))
+        ws.append(weight_reorg(w, l.c, l.n, l.size, min(l.n, tm), min(l.c, tn)))
         bs.append(b)
     W = np.concatenate(ws)
     Bv = np.concatenate(bs)
