@@ -18,8 +18,12 @@ precision = sys.argv[2] if len(sys.argv) > 2 else "int16"
 eb = 2 if precision == "int16" else 4
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
 net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 80))
-pack = yw.synth_pack(net, precision, seed=0)
-y = Yolo2Net(net, pack, max_batch=batch)
+tn = int(os.environ.get("Y2_TN", "4"))          # emulate a reference built with --tn <Y2_TN> (yolo2cuda_set_tile_params)
+pack = yw.synth_pack(net, precision, seed=0, tn=tn)
+from yolo2_b200.accel import Accelerator  # noqa: E402
+acc = Accelerator(0, precision)
+acc.set_tile_params(tn, 32)
+y = Yolo2Net(net, pack, max_batch=batch, accel=acc)
 frames = np.tile(yw.synth_frames(net, 4), (batch // 4 + 1, 1, 1, 1))[:batch]
 for _ in range(2):
     y.forward(frames)
@@ -46,4 +50,4 @@ for i, (l, t) in enumerate(zip(net.layers, ms)):
         r["GBps"] = by / (t * 1e-3) / 1e9
         r["frac_of_hbm_peak"] = r["GBps"] / peaks["hbm_gbs"]
     rows.append(r)
-print(json.dumps({"batch": batch, "precision": precision, "total_ms": tot, "fps": batch / (tot * 1e-3), "layers": rows}, indent=1))
+print(json.dumps({"batch": batch, "precision": precision, "tn": tn, "total_ms": tot, "fps": batch / (tot * 1e-3), "layers": rows}, indent=1))

@@ -437,3 +437,50 @@ def test_tile_param_variants_bit_exact(tn, oracle):
             accel_call(acc, a, x, wr, b, (14, 10, 10, 10))
     finally:
         acc.close()
+
+
+@pytest.mark.parametrize("c,n,k,w,h,q,amp", [
+    (64, 128, 3, 13, 13, (14, 10, 10, 10), 600), (32, 64, 3, 52, 39, (14, 10, 10, 10), 600), (256, 200, 3, 26, 26, (13, 9, 12, 7), 600),
+    (96, 40, 1, 19, 19, (10, 10, 7, 8), 3000), (37, 33, 3, 20, 11, (13, 9, 12, 7), 32767), (16, 130, 3, 21, 9, (4, 10, 6, 12), 32767),
+    (512, 256, 1, 26, 26, (15, 10, 9, 11), 600), (1024, 128, 3, 13, 13, (14, 10, 10, 10), 600)])
+def test_tn32_tensor_core_conv_bit_exact(c, n, k, w, h, q, amp, oracle):
+    """csrc/conv_i16_tc32.cu: with the reference built as Tn = 32 one int8 MMA K slice is one rounding group; same bits as the
+    oracle with TN = 32 (itself pinned against that reference build in tests/test_oracle_vs_ref.py), incl. saturation, ragged
+    channel counts (c % 32 != 0, c < 32), partial pixel tiles and output-channel tiles."""
+    from yolo2_b200.accel import Accelerator
+    acc = Accelerator(0, "int16")
+    try:
+        acc.set_tile_params(32, 32)
+        a, x, wr, b, _ = make_conv_case(c * n + k, c, n, k, 1, w, h, 1, amp=amp, xamp=32767 if amp > 600 else 2000, tn=32)
+        want = oracle_conv(oracle, a, x, wr, b, q)
+        got = accel_call(acc, a, x, wr, b, q)
+        assert acc.last_kernel.startswith("conv_i16_tc32<"), acc.last_kernel
+        assert np.array_equal(valid(got, w), valid(want, w))
+    finally:
+        acc.close()
+
+
+@pytest.mark.parametrize("tn", [8, 32])
+def test_whole_net_rounding_group_variant(tn, oracle):
+    """a whole (thin) YOLOv2 through the network executor emulating a reference built with --tn 8 (generic kernel) and
+    --tn 32 (tensor-core kernel), every layer's ofm and the region tensor bit-exact to the oracle with the same tile parameters"""
+    from yolo2_b200.accel import Accelerator
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 3, channel_div=8))
+    pack = yw.synth_pack(net, "int16", seed=21, table="default", tn=tn)
+    frames = yw.synth_frames(net, 2, seed=4000)
+    acc = Accelerator(0, "int16")
+    acc.set_tile_params(tn, 32)
+    oracle.set_tile_params(tn, 32)
+    y = Yolo2Net(net, pack, max_batch=2, accel=acc)
+    try:
+        region = y.forward(frames)
+        for f in (0, 1):
+            want_region, dumps = oracle.net_forward(net, frames[f], pack, dump_layers=True)
+            for i, want in dumps.items():
+                got = y.layer_output(i, f)
+                assert np.array_equal(valid(got, net.layers[i].out_w), valid(want, net.layers[i].out_w)), (tn, i)
+            assert np.array_equal(region[f].view(np.uint32), want_region.view(np.uint32))
+    finally:
+        oracle.set_tile_params(4, 32)
+        y.close()
+        acc.close()

@@ -117,6 +117,27 @@ int run_conv_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, cons
                 (TN == 4 || (IFM <= TN && IFM <= 4));   // the C4 kernels' rounding group is 4 channels (or all of them when IFM <= 4)
     if (ctx->elem == 2) fast = fast && fast_shift_ok(so);
     ConvFastParams p{};
+    // a reference built with Tn = 32: one MMA K slice is one rounding group (csrc/conv_i16_tc32.cu)
+    const bool tc32 = !fast && !ctx->force_generic && ctx->elem == 2 && ctx->Tn == 32 && TN == (IFM < 32 ? IFM : 32) && IFM > 4 &&
+                      (K == 1 || K == 3) && S == 1 && Pad == K / 2 && Ow == Iw && Oh == Ih && so >= 8 && so <= 16;
+    if (tc32) {
+        int rc;
+        if ((rc = ensure(ctx, ctx->s_c4in, c4_elems(IFM, Ih, Iw) * ctx->elem))) return rc;
+        if ((rc = ensure(ctx, ctx->s_c4out, c4_elems(OFM, Oh, Ow) * ctx->elem))) return rc;
+        if ((rc = ensure(ctx, ctx->s_wprep, wprep_tc32_bytes(IFM, OFM, K)))) return rc;
+        launch_planar_to_c4(Input, ctx->s_c4in.p, 1, IFM, Ih, Iw, 0, 0, ctx->elem, st);
+        launch_wprep_tc32((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, st);
+        p.B = 1; p.H = Ih; p.W = Iw; p.G = ceil_div(IFM, 4); p.OFM = OFM;
+        p.in = ctx->s_c4in.p; p.out = ctx->s_c4out.p; p.w = ctx->s_wprep.p; p.bias = Beta;
+        p.in_frame_stride = 0; p.out_frame_stride = 0;
+        p.so = so; p.sb = sb; p.leaky = IsNL;
+        if (launch_conv_i16_tc32(p, K, IFM, st, &ctx->last_kernel) > 0) {
+            launch_c4_to_planar(ctx->s_c4out.p, Output, 1, OFM, Oh, Ow, 0, 0, ctx->elem, st);
+            ctx->launches += 4;
+            CUDA_OK(ctx, cudaGetLastError());
+            return YOLO2CUDA_SUCCESS;
+        }
+    }
     if (fast) {
         p.B = 1; p.H = Ih; p.W = Iw; p.G = ceil_div(IFM, 4); p.OFM = OFM;
         if (conv_fast_plan(p, K, ctx->elem) == 0) fast = false;
@@ -374,6 +395,7 @@ struct LayerPlan {
     void *w_dev = nullptr;         // device weight layout (fast path)
     void *w_tc = nullptr;          // tcgen05 operand tiles (tensor-core path)
     bool tc = false;
+    bool tc32 = false;             // Tn = 32 build: csrc/conv_i16_tc32.cu
     int Qw = 0, Qa_in = 0, Qa_out = 0, Qb = 0;
     int reorg_shift = 0;
     int region_q = 0;
@@ -448,7 +470,14 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
         if (net->timing) cudaEventRecord(net->ev[i], st);
         switch (l.d.type) {
         case YOLO2CUDA_CONV: {
-            if (l.fast) {
+            if (l.tc32) {
+                ConvFastParams p = l.cp;
+                p.B = B;
+                int n = launch_conv_i16_tc32(p, l.d.size, l.d.c, st, &l.variant);
+                if (n < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "layer %zu: Tn=32 tensor-core conv not eligible", i);
+                launches += n;
+                ctx->last_kernel = l.variant;
+            } else if (l.fast) {
                 ConvFastParams p = l.cp;
                 p.B = B;
                 int n;
@@ -737,6 +766,22 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
             l.fast = !ctx->force_generic && (l.d.size == 1 || l.d.size == 3) && l.d.stride == 1 && l.d.pad == l.d.size / 2 &&
                      l.d.out_w == l.d.w && l.d.out_h == l.d.h && (e == 4 || fast_shift_ok(so)) &&
                      (e == 4 || TN == 4 || l.d.c <= 4);   // int16: the C4 kernels' rounding group is 4 channels
+            l.tc32 = false;
+            if (!l.fast && !ctx->force_generic && e == 2 && ctx->Tn == 32 && l.d.c > 4 && (l.d.size == 1 || l.d.size == 3) &&
+                l.d.stride == 1 && l.d.pad == l.d.size / 2 && l.d.out_w == l.d.w && l.d.out_h == l.d.h && so >= 8 && so <= 16) {
+                // reference built with Tn = 32: tensor-core kernel, one MMA K slice per rounding group
+                ConvFastParams p{};
+                p.B = net->max_batch; p.H = l.d.h; p.W = l.d.w; p.G = ceil_div(l.d.c, 4); p.OFM = l.d.n;
+                if (!l.w_tc && (rc = net_alloc(net, &l.w_tc, wprep_tc32_bytes(l.d.c, l.d.n, l.d.size)))) return rc;
+                launch_wprep_tc32((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, st);
+                ctx->launches += 1;
+                p.in = l.in.base; p.out = l.out.base; p.w = l.w_tc;
+                p.bias = (char *)net->d_bblob + l.b_off * e;
+                p.in_frame_stride = l.in.frame_stride; p.out_frame_stride = l.out.frame_stride;
+                p.so = so; p.sb = l.Qb - l.Qa_out; p.leaky = l.d.leaky;
+                l.cp = p;
+                l.tc32 = true;
+            }
             if (l.fast) {
                 ConvFastParams p{};
                 p.B = net->max_batch; p.H = l.d.h; p.W = l.d.w; p.G = ceil_div(l.d.c, 4); p.OFM = l.d.n;

@@ -1,0 +1,488 @@
+// INT16 convolution on the tensor cores for a reference BUILT with rounding group Tn = 32
+// (scripts/hw_params_gen.py --tn 32), bit-exact to that build.
+//
+// With Tn = 32 one step of the reference's chain (hls/core/core_compute.cpp:65-120) is
+//   acc = clamp16(acc + ((P + half) >> so)),  P = sum_{t<32} w[m][32g+t][tap] * x[32g+t][pixel+tap],
+// i.e. exactly ONE K = 32 slice of an int8 MMA per byte-plane pair: no block-diagonal operand, no wasted K rows, and 8x fewer
+// round-and-saturate steps per MAC than the default Tn = 4 build.  Same decomposition as csrc/conv_i16_tc2.cu:
+//   HH = sum wh*xh,  M = sum (wh*xl + wl*xh),  LL = sum wl*xl,   P = 65536*HH + 256*M + LL   (four tcgen05.mma kind::i8),
+// one TMEM column per (step, pixel).  Per step and output the CUDA cores do
+//   t = 256*M + LL + half;  d = HH * 2^(16-so) + (t >> so);  acc = max(min(acc + d, 65535), 0)      (8 <= so <= 16).
+//
+// Tile = 128 output channels x 32 pixels x one step (N = 32 columns per plane, 96 TMEM columns, five buffers).  A CTA owns 96
+// consecutive pixels = three tiles; tile r of every step belongs to epilogue group r (its 32 accumulators per thread stay in
+// registers for the whole layer), to builder warp r (which gathers the 32 channels of its 32 pixels from the staged C4 patch and
+// writes the hi/lo byte planes of the B operand) and to issuer warp r.  Weights are the A operand from shared memory (one 8 KB
+// canonical tile per step, streamed by cp.async.bulk through a 4-slot ring): with N = 32 the MMA is shared-memory bound at
+// 40 cycles (profiles/microbench/umma_issue.cu), 160 cycles per 4096-step tile, which the ~300-cycle TMEM hand-off loop
+//  hides.  The barrier ring has 12 = 4 steps x 3 tiles slots: slot -> fixed tile index r, so every barrier's
+// consecutive phases are awaited by the same warp.
+#include "common.cuh"
+
+namespace y2 {
+
+namespace {
+
+constexpr int kM = 128;             // output channels per CTA = TMEM lanes
+constexpr int kN = 32;              // pixels per tile = MMA N
+constexpr int kR = 3;               // tiles per step -> 96 pixels per CTA; tile r <-> epilogue group r, builder r, issuer r
+constexpr int kPT = kN * kR;
+constexpr int kBufs = 5;            // TMEM accumulator buffers: HH | M | LL, 32 columns each
+constexpr int kBufCols = 3 * kN;
+constexpr int kRing = 12;           // activation tile ring (hi 1 KB | lo 1 KB) and barrier ring: 4 steps x 3 tiles
+constexpr int kWRing = 4;           // weight ring: one 8 KB step tile per slot (hi 4 KB | lo 4 KB, canonical K-major)
+constexpr int kEpiWarps = 12;       // warps 0-11: group kg = warp/4, TMEM lane quadrant = warp%4
+constexpr int kBuilder = 12;        // warps 12-14
+constexpr int kLoader = 15;         // warp 15: weight ring
+constexpr int kIssuer = 16;         // warps 16-18; warp 19 idles
+constexpr int kThreads = 20 * 32;
+constexpr int kEpiRegs = 120, kHelperRegs = 56;   // setmaxnreg (see conv_i16_tc2.cu): 8 x 32 x (96-56) = 10240 >= 12 x 32 x (120-96) = 9216
+constexpr int kWBytes = 2 * kM * 32;
+constexpr int kBBytes = kN * 32;    // one plane of one activation tile
+static_assert(kRing % kR == 0 && kRing % kBufs != 0, "slot -> fixed tile index");
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ unsigned mbar_test(void *bar, unsigned parity)   // non-blocking probe
+{
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_arrive(void *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(void *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_i8_ss(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, int *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const uint4 &a, const uint4 &b)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(a.x), "r"(a.y), "r"(a.z),
+                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+// ties the registers of an asynchronous tcgen05.ld to the point after tcgen05.wait::ld
+__device__ __forceinline__ void reg_fence16(int *r)
+{
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// K-major, no-swizzle canonical operand: core matrix = 8 rows x 16 bytes, contiguous (128 B);
+// the two K chunks of a 32-byte row are LBO = 128 B apart, 8-row groups are SBO = 256 B apart.
+__device__ __forceinline__ unsigned long long smem_desc(const void *p)
+{
+    unsigned long long d = (unsigned long long)((smem_u32(p) >> 4) & 0x3FFF);
+    d |= (unsigned long long)(128 >> 4) << 16;
+    d |= (unsigned long long)(256 >> 4) << 32;
+    d |= 1ull << 46;  // descriptor version for sm_100
+    return d;
+}
+__host__ __device__ constexpr unsigned idesc_i8(int a_signed, int b_signed)
+{
+    return (2u << 4) | ((unsigned)a_signed << 7) | ((unsigned)b_signed << 10) | ((unsigned)(kN >> 3) << 17) | ((unsigned)(kM >> 4) << 24);
+}
+__host__ __device__ inline int operand_off(int row, int k) { return (((row >> 3) * 2 + (k >> 4)) * 8 + (row & 7)) * 16 + (k & 15); }
+
+
+struct Tc32Params {
+    const uint2 *in;          // C4 input
+    int16_t *out;             // C4 output (already offset to the first output group)
+    const unsigned char *w;   // [mtile][step][hi 4 KB | lo 4 KB] canonical operand tiles
+    const int16_t *bias;
+    int B, H, W, G, OFM;      // G = C4 groups of the input
+    long long in_frame_stride, out_frame_stride;  // elements
+    int sb, leaky;
+    int nsteps;               // ceil(IFM/32) * K*K
+    int PW, rows_max, gs_shift;  // staging: smem row pitch (pixels), band rows incl. halo + zero row, log2(C4 groups per chunk) >= 3
+};
+
+template <int SO>
+__device__ __forceinline__ int tc32_step(int acc, int hh, int mm, int ll)
+{
+    const int t = mm * 256 + ll + (1 << (SO - 1));         // P + half without its 65536*HH part
+    const int d = hh * (1 << (16 - SO)) + (t >> SO);       // 65536*HH is a multiple of 2^so
+    return __viaddmin_s32_relu(acc, d, 65535);
+}
+
+template <int KS, int SO>
+__global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Params p)
+{
+    constexpr int K2 = KS * KS;
+    constexpr int PAD = KS / 2;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *sW = smem;                                    // kWRing x 8 KB
+    unsigned char *sB = sW + kWRing * kWBytes;                   // kRing x (hi 1 KB | lo 1 KB)
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sB + kRing * 2 * kBBytes);
+    unsigned long long *w_full = bars, *w_empty = w_full + kWRing, *go = w_empty + kWRing, *mma_done = go + kRing;
+    // go[slot]: the tile in this ring slot may be issued = its activation tile is built (1 arrival, builder) AND its TMEM buffer
+    // it % 5 has been read out by the epilogue of tile it-5 (4 arrivals; pre-arrived for the first five tiles)
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(mma_done + kRing + 1);
+    int *pxtab = reinterpret_cast<int *>(tmem_slot + 4);         // [96][4]: smem pixel offset for tap rows 0..2, valid flag
+    uint2 *sX = reinterpret_cast<uint2 *>(pxtab + kPT * 4);      // 2 chunks x GS groups x rows_max x PW pixels
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long npix = (long long)p.B * p.H * p.W;
+    const long long pix0 = (long long)blockIdx.x * kPT;
+    const int mtile = blockIdx.y;
+    const int zero_slot = p.rows_max - 1;
+    const int GS = 1 << p.gs_shift;
+    const int chunk_px = GS * p.rows_max * p.PW;
+    const long long row_first = pix0 / p.W;                      // global row (frame*H + y) of the first pixel
+
+    if (tid == 0) {
+        for (int i = 0; i < kWRing; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], kR); }
+        for (int i = 0; i < kRing; ++i) { mbar_init(&go[i], 5); mbar_init(&mma_done[i], 1); }
+        for (int i = 0; i < kBufs; ++i)
+            for (int k = 0; k < 4; ++k) mbar_arrive(&go[i]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kIssuer) {   // the first MMA warp owns the TMEM allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int q = tid; q < kPT; q += kThreads) {
+        long long gp = pix0 + q;
+        int valid = gp < npix;
+        long long grow = valid ? gp / p.W : row_first;
+        int x = valid ? (int)(gp - grow * p.W) : 0;
+        int y = (int)(grow % p.H);
+        int rl = (int)(grow - row_first);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            int yin = y + i - PAD;
+            int slot = (valid && i < KS && yin >= 0 && yin < p.H) ? rl + i : zero_slot;
+            pxtab[q * 4 + i] = slot * p.PW + x;
+        }
+        pxtab[q * 4 + 3] = valid;
+    }
+    for (int i = tid; i < 2 * chunk_px; i += kThreads) sX[i] = make_uint2(0u, 0u);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const unsigned tmem = *tmem_slot;
+
+    if (warp >= kEpiWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHelperRegs));
+        if (warp >= kIssuer) {
+            // ===== three MMA issuer warps: warp iw issues tile iw of every step =====
+            const int iw = warp - kIssuer;
+            if (iw < kR) {
+                const unsigned long long dA0 = smem_desc(sW), dB0 = smem_desc(sB);
+                constexpr unsigned long long kAStep = kWBytes >> 4, kAPlane = (kM * 32) >> 4;      // descriptor address units (16 B)
+                constexpr unsigned long long kBStep = (2 * kBBytes) >> 4, kBPlane = kBBytes >> 4;
+                unsigned elected;
+                asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
+                int slot = iw, sph = 0, tb = iw;                 // ring slot it % 12 + its phase parity, TMEM buffer it % 5 (it = 3 s + iw)
+                for (int s = 0; s < p.nsteps; ++s) {
+                    const int ws = s % kWRing;
+                    mbar_wait(&w_full[ws], (s / kWRing) & 1);
+                    mbar_wait(&go[slot], sph);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    if (elected) {
+                        const unsigned long long dAh = dA0 + ws * kAStep, dAl = dAh + kAPlane;
+                        const unsigned long long dBh = dB0 + slot * kBStep, dBl = dBh + kBPlane;
+                        const unsigned d0 = tmem + tb * kBufCols;
+                        umma_i8_ss(d0, dAh, dBh, idesc_i8(1, 1), 0);            // HH
+                        umma_i8_ss(d0 + kN, dAh, dBl, idesc_i8(1, 0), 0);       // M  = hi*lo
+                        umma_i8_ss(d0 + kN, dAl, dBh, idesc_i8(0, 1), 1);       //    + lo*hi
+                        umma_i8_ss(d0 + 2 * kN, dAl, dBl, idesc_i8(0, 0), 0);   // LL
+                        umma_commit(&mma_done[slot]);                           // epilogue (tile ready) and builder (slot free)
+                        umma_commit(&w_empty[ws]);                              // this warp's reads of the step's weights are done
+                    }
+                    __syncwarp();
+                    slot += kR;
+                    if (slot >= kRing) { slot -= kRing; sph ^= 1; }
+                    tb = tb >= kBufs - kR ? tb - (kBufs - kR) : tb + kR;
+                }
+            }
+        } else if (warp == kLoader) {
+            // ===== weight ring: one 8 KB bulk copy per step =====
+            if (lane == 0) {
+                const unsigned char *src = p.w + (size_t)mtile * p.nsteps * kWBytes;
+                for (int s = 0; s < p.nsteps; ++s) {
+                    const int ws = s % kWRing;
+                    if (s >= kWRing) mbar_wait(&w_empty[ws], ((s / kWRing) - 1) & 1);
+                    mbar_expect_tx(&w_full[ws], kWBytes);
+                    bulk_g2s(sW + ws * kWBytes, src + (size_t)s * kWBytes, kWBytes, &w_full[ws]);
+                }
+            }
+        } else {
+            // ===== three builder warps: stage activations (cp.async); lane = one pixel of tile bw, it gathers the 32 channels of the
+            // step's group (eight C4 words) and writes the hi / lo byte planes of the B operand (row = pixel, K = channel) =====
+            const int bw = warp - kBuilder;
+            const int bt = bw * 32 + lane;              // 0..95 = the CTA pixel this lane owns
+            constexpr int kBT = kR * 32;
+            const int nrows = p.rows_max - 1;           // staged band rows (the last slot is the all-zero row)
+            const int nchunks = (p.G + GS - 1) >> p.gs_shift;
+            auto stage_chunk = [&](int c) {
+                uint2 *dst = sX + (c & 1) * chunk_px;
+                const int g0 = c << p.gs_shift, ng = min(GS, p.G - g0);
+                const int per_group = nrows * p.W;
+                for (int idx = bt; idx < ng * per_group; idx += kBT) {
+                    int gg = idx / per_group, rem = idx - gg * per_group;
+                    int s = rem / p.W, x = rem - s * p.W;
+                    long long Rr = row_first - PAD + s;
+                    if (Rr >= 0 && Rr < (long long)p.B * p.H) {
+                        long long ff = Rr / p.H;
+                        int yy = (int)(Rr - ff * p.H);
+                        const uint2 *src = p.in + ff * (p.in_frame_stride >> 2) + ((long long)(g0 + gg) * p.H + yy) * p.W + x;
+                        cp_async8(dst + (gg * p.rows_max + s) * p.PW + PAD + x, src);
+                    }
+                }
+                asm volatile("cp.async.commit_group;");
+            };
+            const int r0 = operand_off(lane, 0), r1 = operand_off(lane, 16);   // this pixel's two 16-byte K chunks
+            int pxo[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) pxo[i] = pxtab[bt * 4 + i];
+            stage_chunk(0);
+            int staged = 0, ready = -1;
+            int slot = bw, sph = 0;
+            for (int s = 0; s < p.nsteps; ++s) {
+                const int g32 = s / K2, tap = s - g32 * K2;
+                const int ti = tap / KS, tj = tap - ti * KS;
+                const int c_need = (8 * g32) >> p.gs_shift;      // the chunk holding this step's eight C4 groups
+                if (staged + 1 < nchunks && staged <= c_need) {
+                    bar_sync_named(1, kBT);             // every builder is past the steps of chunk staged-1
+                    stage_chunk(staged + 1);
+                    ++staged;
+                }
+                if (ready < c_need) {
+                    if (staged > c_need) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    bar_sync_named(1, kBT);             // all builder warps see each other's copies
+                    ready = c_need;
+                }
+                if (s >= kRing / kR) mbar_wait(&mma_done[slot], sph ^ 1);   // the MMAs of the previous tile in this slot have read it
+                const uint2 *xs = sX + (c_need & 1) * chunk_px + ((8 * g32) & (GS - 1)) * p.rows_max * p.PW + pxo[ti] + tj;
+                unsigned hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint2 x = make_uint2(0u, 0u);
+                    if (8 * g32 + j < p.G) x = xs[j * p.rows_max * p.PW];
+                    hi[j] = __byte_perm(x.x, x.y, 0x7531);
+                    lo[j] = __byte_perm(x.x, x.y, 0x6420);
+                }
+                unsigned char *bh = sB + (slot * 2) * kBBytes;
+                *reinterpret_cast<uint4 *>(bh + r0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(bh + r1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                *reinterpret_cast<uint4 *>(bh + kBBytes + r0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4 *>(bh + kBBytes + r1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&go[slot]);
+                slot += kR;
+                if (slot >= kRing) { slot -= kRing; sph ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps: thread = one output channel (TMEM lane); group kg = warp/4 owns tile kg (32 pixels) of every step =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
+        const int q4 = warp & 3, kg = warp >> 2;
+        const int m = mtile * kM + q4 * 32 + lane;
+        const unsigned lane_base = tmem + ((unsigned)(q4 * 32) << 16);
+        int U[kN];
+        {
+            long long bv = (m < p.OFM) ? (long long)p.bias[m] : 0;
+            long long bs = round_shift64(bv, p.sb);
+            const long long rb = (1LL << (38 - SO)) + 2;      // |(P + half) >> so| <= 2^(38-so) for 32 products: clamping the bias term there cannot change clamp16(bias + r)
+            long long boff = bs + 32768;
+            if (boff > 65535 + rb) boff = 65535 + rb;
+            if (boff < -rb) boff = -rb;
+#pragma unroll
+            for (int j = 0; j < kN; ++j) U[j] = (int)boff;
+        }
+        int slot = kg, sph = 0, tb = kg;
+        for (int s = 0; s < p.nsteps; ++s) {
+            mbar_wait(&mma_done[slot], sph);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const unsigned base = lane_base + tb * kBufCols;
+            int hh[16], mm[16], ll[16];
+            tmem_ld16(base, hh); tmem_ld16(base + kN, mm); tmem_ld16(base + 2 * kN, ll);          // pixels 0-15
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            reg_fence16(hh); reg_fence16(mm); reg_fence16(ll);
+#pragma unroll
+            for (int n = 0; n < 16; ++n) U[n] = tc32_step<SO>(U[n], hh[n], mm[n], ll[n]);
+            tmem_ld16(base + 16, hh); tmem_ld16(base + kN + 16, mm); tmem_ld16(base + 2 * kN + 16, ll);   // pixels 16-31
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            reg_fence16(hh); reg_fence16(mm); reg_fence16(ll);
+            // the whole tile has been read: hand the TMEM buffer to tile it+5
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&go[slot + kBufs < kRing ? slot + kBufs : slot + kBufs - kRing]);
+#pragma unroll
+            for (int n = 0; n < 16; ++n) U[16 + n] = tc32_step<SO>(U[16 + n], hh[n], mm[n], ll[n]);
+            slot += kR;
+            if (slot >= kRing) { slot -= kRing; sph ^= 1; }
+            tb = tb >= kBufs - kR ? tb - (kBufs - kR) : tb + kR;
+        }
+        if (m < p.OFM) {
+#pragma unroll
+            for (int j = 0; j < kN; ++j) {
+                const long long gp = pix0 + kg * kN + j;
+                if (gp >= npix) continue;
+                const long long grow = gp / p.W;
+                const int x = (int)(gp - grow * p.W);
+                const long long f = grow / p.H;
+                const int y = (int)(grow - f * p.H);
+                int a = U[j] - 32768;
+                if (p.leaky && a < 0) a = a / 10;
+                p.out[f * p.out_frame_stride + (((long long)(m >> 2) * p.H + y) * p.W + x) * 4 + (m & 3)] = (int16_t)a;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == kIssuer) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+// Weight tiles from one layer of the reference's reorganised blob (addressed with the build's TM / TN = 32):
+// [mtile][step = (32-channel group, tap)][plane hi | lo][canonical 128 rows x 32 K-bytes].
+__global__ void wprep_tc32_kernel(const int16_t *__restrict__ blob, unsigned char *__restrict__ dst, int ifm, int ofm, int ksize,
+                                  int TM, int TN, int nsteps, long long total)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int k2 = ksize * ksize;
+    int k = idx & 31;
+    long long r = idx >> 5;
+    int ml = r % kM; r /= kM;
+    int s = r % nsteps;
+    int mtile = r / nsteps;
+    int m = mtile * kM + ml;
+    int g32 = s / k2, tap = s - g32 * k2, c = g32 * 32 + k;
+    int hi = 0, lo = 0;
+    if (m < ofm && c < ifm) {
+        int w = blob[reorg_woff(m, c, tap, ifm, ofm, k2, TM, TN)];
+        hi = (w >> 8) & 0xff;
+        lo = w & 0xff;
+    }
+    unsigned char *tile = dst + ((size_t)mtile * nsteps + s) * kWBytes;
+    tile[operand_off(ml, k)] = (unsigned char)hi;
+    tile[kM * 32 + operand_off(ml, k)] = (unsigned char)lo;
+}
+
+template <int KS, int SO>
+void launch_one(const Tc32Params &p, dim3 grid, size_t smem, cudaStream_t st)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(conv_i16_tc32_kernel<KS, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        configured = true;
+    }
+    conv_i16_tc32_kernel<KS, SO><<<grid, kThreads, smem, st>>>(p);
+}
+
+template <int KS>
+bool dispatch_so(const Tc32Params &p, int so, dim3 grid, size_t smem, cudaStream_t st)
+{
+    switch (so) {
+#define Y2_TC32_CASE(S) case S: launch_one<KS, S>(p, grid, smem, st); return true;
+        Y2_TC32_CASE(8) Y2_TC32_CASE(9) Y2_TC32_CASE(10) Y2_TC32_CASE(11) Y2_TC32_CASE(12) Y2_TC32_CASE(13) Y2_TC32_CASE(14)
+        Y2_TC32_CASE(15) Y2_TC32_CASE(16)
+#undef Y2_TC32_CASE
+    default: return false;
+    }
+}
+
+}  // namespace
+
+size_t wprep_tc32_bytes(int ifm, int ofm, int ksize)
+{
+    return (size_t)ceil_div(ofm, kM) * ceil_div(ifm, 32) * ksize * ksize * kWBytes;
+}
+
+void launch_wprep_tc32(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, cudaStream_t st)
+{
+    const int nsteps = ceil_div(ifm, 32) * ksize * ksize;
+    const long long total = (long long)ceil_div(ofm, kM) * nsteps * kM * 32;
+    wprep_tc32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(blob, (unsigned char *)dst, ifm, ofm, ksize, TM, TN, nsteps, total);
+}
+
+// Returns 1 when launched, -1 when the shape/shift is not eligible.
+int launch_conv_i16_tc32(const ConvFastParams &cp, int ksize, int ifm, cudaStream_t st, const char **variant)
+{
+    if ((ksize != 1 && ksize != 3) || cp.so < 8 || cp.so > 16) return -1;
+    Tc32Params p{};
+    p.in = (const uint2 *)cp.in; p.out = (int16_t *)cp.out; p.w = (const unsigned char *)cp.w; p.bias = (const int16_t *)cp.bias;
+    p.B = cp.B; p.H = cp.H; p.W = cp.W; p.G = cp.G; p.OFM = cp.OFM;
+    p.in_frame_stride = cp.in_frame_stride; p.out_frame_stride = cp.out_frame_stride;
+    p.sb = cp.sb; p.leaky = cp.leaky;
+    p.nsteps = ceil_div(ifm, 32) * ksize * ksize;
+    p.PW = cp.W + ksize - 1;
+    p.rows_max = (kPT - 1) / cp.W + 2 + (ksize - 1) + 1;
+    const size_t fixed = (size_t)kWRing * kWBytes + (size_t)kRing * 2 * kBBytes + 512 + kPT * 16;
+    const size_t per_group = (size_t)p.rows_max * p.PW * 8;
+    int gs = (int)((200 * 1024 - fixed) / (2 * per_group));
+    if (gs < 8) return -1;                              // a chunk must hold the eight C4 groups of one 32-channel rounding group
+    int sh = 3;
+    while ((2 << sh) <= gs && (2 << sh) <= 16) ++sh;    // largest power of two <= min(gs, 16)
+    p.gs_shift = sh;
+    gs = 1 << sh;
+    size_t smem = fixed + 2 * per_group * gs + 1024;
+    if (smem < 120 * 1024) smem = 120 * 1024;           // one CTA per SM: a CTA allocates all 512 TMEM columns
+    dim3 grid((unsigned)(((long long)cp.B * cp.H * cp.W + kPT - 1) / kPT), ceil_div(cp.OFM, kM));
+    const bool ok = ksize == 3 ? dispatch_so<3>(p, cp.so, grid, smem, st) : dispatch_so<1>(p, cp.so, grid, smem, st);
+    if (!ok) return -1;
+    if (variant) *variant = ksize == 3 ? "conv_i16_tc32<3>" : "conv_i16_tc32<1>";
+    return 1;
+}
+
+}  // namespace y2
