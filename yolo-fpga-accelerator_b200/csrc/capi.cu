@@ -26,7 +26,8 @@ struct yolo2cuda_ctx {
     const char *last_kernel = "";
     int force_generic = 0;
     int Tn = YOLO2CUDA_Tn, Tm = YOLO2CUDA_Tm;   // tile parameters of the emulated reference build (yolo2cuda_set_tile_params)
-    int use_tc = 0;   // YOLO2CUDA_TC=1: tcgen05 conv (csrc/conv_i16_tc.cu) where eligible
+    int use_tc = -1;  // YOLO2CUDA_TC: unset = auto (network executor uses csrc/conv_i16_tc2.cu on the layers where it is faster),
+                      // 0 = CUDA-core kernels only, 1 = csrc/conv_i16_tc.cu, 2 = csrc/conv_i16_tc2.cu wherever eligible
     int tc_min_ofm = 96;
     // growable device scratch for the per-layer entry points
     struct Scratch { void *p = nullptr; size_t bytes = 0; } s_in, s_out, s_w, s_b, s_c4in, s_c4out, s_wprep;
@@ -157,7 +158,7 @@ int run_conv_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, cons
     int rc;
     if ((rc = ensure(ctx, ctx->s_c4in, c4_elems(IFM, Ih, Iw) * ctx->elem))) return rc;
     if ((rc = ensure(ctx, ctx->s_c4out, c4_elems(OFM, Oh, Ow) * ctx->elem))) return rc;
-    const bool tc = ctx->use_tc && ctx->elem == 2 && so >= 8 && so <= 22;
+    const bool tc = ctx->use_tc > 0 && ctx->elem == 2 && so >= 8 && so <= 22;   // (auto mode: single-frame calls stay on the CUDA cores)
     const bool tc2 = tc && ctx->use_tc == 2;
     if ((rc = ensure(ctx, ctx->s_wprep, tc2 ? wprep_tc2_bytes(IFM, OFM, K) : tc ? wprep_tc_bytes(IFM, OFM, K) : wprep_bytes(IFM, OFM, K, ctx->elem)))) return rc;
     launch_planar_to_c4(Input, ctx->s_c4in.p, 1, IFM, Ih, Iw, 0, 0, ctx->elem, st);
@@ -219,7 +220,7 @@ int yolo2cuda_create(yolo2cuda_ctx **out, int device, int precision)
     const char *fg = getenv("YOLO2CUDA_FORCE_GENERIC");
     ctx->force_generic = (fg && fg[0] && fg[0] != '0') ? 1 : 0;
     const char *tc = getenv("YOLO2CUDA_TC");
-    ctx->use_tc = (tc && tc[0] && tc[0] != '0') ? (tc[0] == '2' ? 2 : 1) : 0;   // 1: csrc/conv_i16_tc.cu, 2: csrc/conv_i16_tc2.cu
+    ctx->use_tc = (tc && tc[0]) ? (tc[0] == '0' ? 0 : tc[0] == '2' ? 2 : 1) : -1;
     if (const char *mo = getenv("YOLO2CUDA_TC_MIN_OFM")) ctx->tc_min_ofm = atoi(mo);
     *out = ctx;
     return YOLO2CUDA_SUCCESS;
@@ -483,7 +484,7 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
                 int n;
                 if (l.tc) {
                     p.w = l.w_tc;
-                    n = ctx->use_tc == 2 ? launch_conv_i16_tc2(p, l.d.size, st, &l.variant) : launch_conv_i16_tc(p, l.d.size, st, &l.variant);
+                    n = ctx->use_tc != 1 ? launch_conv_i16_tc2(p, l.d.size, st, &l.variant) : launch_conv_i16_tc(p, l.d.size, st, &l.variant);
                 } else {
                     n = e == 2 ? launch_conv_i16_fast(p, l.d.size, st, &l.variant) : launch_conv_f32_fast(p, l.d.size, st, &l.variant);
                 }
@@ -797,9 +798,14 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                     p.so = so > 30 ? 30 : so; p.sb = l.Qb - l.Qa_out; p.leaky = l.d.leaky;
                     l.cp = p;
                     // tensor-core path: wide layers only (a CTA covers 128 output channels)
-                    l.tc = ctx->use_tc && e == 2 && so >= 8 && so <= 22 && l.d.n >= ctx->tc_min_ofm;
+                    l.tc = ctx->use_tc > 0 && e == 2 && so >= 8 && so <= 22 && l.d.n >= ctx->tc_min_ofm;
+                    // auto: the tcgen05 kernel where it measured faster than the CUDA-core kernel (profiles/r1_layer_table_int16_b256_tc2.json):
+                    // full 128-channel tiles on the narrow (<= 26 wide) deep layers; both paths are bit-exact, so mixing them is safe
+                    if (ctx->use_tc < 0 && e == 2 && so >= 8 && so <= 22 && l.d.n % 128 == 0 && l.d.c >= 128 &&
+                        ((l.d.size == 3 && l.d.w <= 26) || (l.d.size == 1 && l.d.w <= 13)))
+                        l.tc = true;
                     if (l.tc) {
-                        const bool v2 = ctx->use_tc == 2;
+                        const bool v2 = ctx->use_tc != 1;
                         if (!l.w_tc && (rc = net_alloc(net, &l.w_tc, v2 ? wprep_tc2_bytes(l.d.c, l.d.n, l.d.size) : wprep_tc_bytes(l.d.c, l.d.n, l.d.size)))) return rc;
                         if (v2) launch_wprep_tc2((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, so, st);
                         else launch_wprep_tc((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, so, st);

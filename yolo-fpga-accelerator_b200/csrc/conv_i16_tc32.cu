@@ -150,6 +150,7 @@ struct Tc32Params {
     long long in_frame_stride, out_frame_stride;  // elements
     int sb, leaky;
     int nsteps;               // ceil(IFM/32) * K*K
+    int ctab_cap;             // entries reserved for the activation copy table
     int PW, rows_max, gs_shift;  // staging: smem row pitch (pixels), band rows incl. halo + zero row, log2(C4 groups per chunk) >= 3
 };
 
@@ -175,7 +176,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
     // it % 5 has been read out by the epilogue of tile it-5 (4 arrivals; pre-arrived for the first five tiles)
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(mma_done + kRing + 1);
     int *pxtab = reinterpret_cast<int *>(tmem_slot + 4);         // [96][4]: smem pixel offset for tap rows 0..2, valid flag
-    uint2 *sX = reinterpret_cast<uint2 *>(pxtab + kPT * 4);      // 2 chunks x GS groups x rows_max x PW pixels
+    int *rowinfo = pxtab + kPT * 4;                              // [32][2]: per staged row slot: first needed column, prefix of the copy table
+    int2 *ctab = reinterpret_cast<int2 *>(rowinfo + 64);         // copy table of one C4 group plane: (global pixel offset, smem pixel offset)
+    uint2 *sX = reinterpret_cast<uint2 *>(ctab + p.ctab_cap);    // 2 chunks x GS groups x rows_max x PW pixels
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long npix = (long long)p.B * p.H * p.W;
@@ -211,6 +214,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
             pxtab[q * 4 + i] = slot * p.PW + x;
         }
         pxtab[q * 4 + 3] = valid;
+    }
+    // Activation copy table.  Staged row slot s holds global row row_first - PAD + s; only the columns some pixel of this CTA reads
+    // are copied (a CTA's pixels are consecutive, so on wide images it touches a fraction of each row), and the loader walks a
+    // precomputed (source, destination) list instead of doing index arithmetic per element.
+    if (tid == 0) {
+        const long long pix_last = (pix0 + kPT < npix ? pix0 + kPT : npix) - 1;
+        const long long row_last = pix_last / p.W;
+        const int nrow_cta = (int)(row_last - row_first) + 1;
+        const int x_first = (int)(pix0 - row_first * p.W), x_last = (int)(pix_last - row_last * p.W);
+        int total = 0;
+        for (int s = 0; s < p.rows_max - 1; ++s) {
+            int lo = p.W, hi = -1;
+            const long long Rr = row_first - PAD + s;
+            if (Rr >= 0 && Rr < (long long)p.B * p.H)
+                for (int i = 0; i < KS; ++i) {
+                    const int j = s - i;
+                    if (j < 0 || j >= nrow_cta) continue;
+                    const int xa = (j == 0 ? x_first : 0) - PAD, xb = (j == nrow_cta - 1 ? x_last : p.W - 1) + PAD;
+                    lo = min(lo, max(xa, 0));
+                    hi = max(hi, min(xb, p.W - 1));
+                }
+            rowinfo[2 * s] = lo;
+            rowinfo[2 * s + 1] = total;
+            total += hi >= lo ? hi - lo + 1 : 0;
+        }
+        rowinfo[2 * (p.rows_max - 1)] = 0;
+        rowinfo[2 * (p.rows_max - 1) + 1] = total;      // = entries per C4 group plane
+    }
+    __syncthreads();
+    for (int idx = tid; idx < (p.rows_max - 1) * p.W; idx += kThreads) {
+        const int s = idx / p.W, x = idx - s * p.W;
+        const int lo = rowinfo[2 * s], cnt = rowinfo[2 * s + 3] - rowinfo[2 * s + 1];
+        if (x < lo || x >= lo + cnt) continue;
+        const long long Rr = row_first - PAD + s;
+        const long long ff = Rr / p.H;
+        const int yy = (int)(Rr - ff * p.H);
+        ctab[rowinfo[2 * s + 1] + x - lo] = make_int2((int)(ff * (p.in_frame_stride >> 2)) + yy * p.W + x, s * p.PW + PAD + x);
     }
     for (int i = tid; i < 2 * chunk_px; i += kThreads) sX[i] = make_uint2(0u, 0u);
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -274,17 +314,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
             auto stage_chunk = [&](int c) {
                 uint2 *dst = sX + (c & 1) * chunk_px;
                 const int g0 = c << p.gs_shift, ng = min(GS, p.G - g0);
-                const int per_group = nrows * p.W;
+                const int per_group = rowinfo[2 * (p.rows_max - 1) + 1];
+                const long long plane = (long long)p.H * p.W;
                 for (int idx = bt; idx < ng * per_group; idx += kBT) {
-                    int gg = idx / per_group, rem = idx - gg * per_group;
-                    int s = rem / p.W, x = rem - s * p.W;
-                    long long Rr = row_first - PAD + s;
-                    if (Rr >= 0 && Rr < (long long)p.B * p.H) {
-                        long long ff = Rr / p.H;
-                        int yy = (int)(Rr - ff * p.H);
-                        const uint2 *src = p.in + ff * (p.in_frame_stride >> 2) + ((long long)(g0 + gg) * p.H + yy) * p.W + x;
-                        cp_async8(dst + (gg * p.rows_max + s) * p.PW + PAD + x, src);
-                    }
+                    const int gg = idx / per_group;
+                    const int2 e = ctab[idx - gg * per_group];
+                    cp_async8(dst + gg * p.rows_max * p.PW + e.y, p.in + (g0 + gg) * plane + e.x);
                 }
                 asm volatile("cp.async.commit_group;");
             };
@@ -468,7 +503,9 @@ int launch_conv_i16_tc32(const ConvFastParams &cp, int ksize, int ifm, cudaStrea
     p.nsteps = ceil_div(ifm, 32) * ksize * ksize;
     p.PW = cp.W + ksize - 1;
     p.rows_max = (kPT - 1) / cp.W + 2 + (ksize - 1) + 1;
-    const size_t fixed = (size_t)kWRing * kWBytes + (size_t)kRing * 2 * kBBytes + 512 + kPT * 16;
+    if (p.rows_max > 30) return -1;                     // rowinfo[] holds 32 staged rows
+    p.ctab_cap = (p.rows_max - 1) * cp.W;
+    const size_t fixed = (size_t)kWRing * kWBytes + (size_t)kRing * 2 * kBBytes + 512 + kPT * 16 + 256 + (size_t)p.ctab_cap * 8;
     const size_t per_group = (size_t)p.rows_max * p.PW * 8;
     int gs = (int)((200 * 1024 - fixed) / (2 * per_group));
     if (gs < 8) return -1;                              // a chunk must hold the eight C4 groups of one 32-channel rounding group
