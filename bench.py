@@ -242,14 +242,17 @@ def main():
     peaks, peak_src = load_peaks()
     int8_peak_tops = 2.0 * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])   # kernel timed inside a long step
     achieved_tops = conv3_macs * 8 * last_chunk / (conv3_ms * 1e-3) / 1e12          # 4 int8 MACs per int16 MAC, 2 OP each
-    roofline = {"bound": "tensor", "kernel": "conv_i16_c4<13,3> (all 3x3 conv layers)", "achieved": achieved_tops,
+    roofline = {"bound": "tensor", "kernel": "all 3x3 conv layers: conv_i16_tc2<3> (tcgen05, 13x13 / 26x26 layers) + conv_i16_c4<13,3> (CUDA cores, wider layers)",
+                "achieved": achieved_tops,
                 "peak": int8_peak_tops, "unit": "TFLOP/s", "frac": achieved_tops / int8_peak_tops,
                 "peak_source": f"2 x bf16_tflops_sustained of {peak_src} MEASURED_PEAKS.json (int8 dense = 2 x bf16)",
                 "traffic": None, "launches_per_step": len(conv3) * chunks, "avg_launch_ms": conv3_ms / len(conv3),
                 "share_of_step": conv3_ms / all_ms,
                 "exact_steps_per_s": conv3_steps * last_chunk / (conv3_ms * 1e-3),
-                "note": "the reference rounds+saturates every 4 MACs, so the bit-exact datapath is integer-ALU-issue bound "
-                        "(7 SASS instr per step); see DESIGN.md 'exactness-adjusted roofline' and profiles/"}
+                "note": "the reference rounds+saturates every 4 MACs (Tn=4), so the bit-exact datapath is bound by the CUDA-core "
+                        "round-and-saturate step (4 SASS instr per step behind the tensor cores, 7 without), not by the tensor pipe; "
+                        "see DESIGN.md 'exactness-adjusted roofline' and profiles/.  A reference built with Tn=32 runs at "
+                        "~2.9 k frames/s on the same kernels' Tn=32 variant (profiles/r1_layer_table_int16_b256_tn32.json)"}
 
     for _ in range(2):
         step_e2e()
