@@ -19,6 +19,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line (NCCL prints its version banner there otherwise)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "yolo-fpga-accelerator_b200"))
 
