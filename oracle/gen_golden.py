@@ -122,9 +122,29 @@ def gen_letterbox():
     print("letterbox.npz", os.path.getsize(os.path.join(OUT, "letterbox.npz")) >> 10, "KiB")
 
 
+VARIANTS = [  # (tn, c, n, size, w, h, q, amp): YOLO2_FPGA of the reference BUILT with --tn <tn> (oracle/Makefile ref-variants)
+    (8, 24, 40, 3, 13, 13, (14, 10, 10, 10), 600), (8, 37, 33, 1, 20, 11, (13, 9, 12, 7), 32767),
+    (32, 64, 128, 3, 13, 13, (14, 10, 10, 10), 600), (32, 37, 130, 3, 20, 11, (13, 9, 12, 7), 32767), (32, 96, 40, 1, 19, 19, (10, 10, 7, 8), 3000)]
+
+
+def gen_variants():
+    os.makedirs(OUT, exist_ok=True)
+    blob = {}
+    for i, (tn, c, n, size, w, h, q, amp) in enumerate(VARIANTS):
+        a, x, wr, b, _ = make_conv_case(500 + i, c, n, size, 1, w, h, 1, amp=amp, xamp=32767 if amp > 600 else 2000, tn=tn)
+        out = Ref("int16", tn).run_layer(x, wr, b, a, q)
+        blob.update({f"v_{i}_x": x, f"v_{i}_w": wr, f"v_{i}_b": b, f"v_{i}_args": args_array(a), f"v_{i}_q": np.array(q, np.int32),
+                     f"v_{i}_tn": np.array([tn], np.int32), f"v_{i}_out": out})
+    np.savez_compressed(os.path.join(OUT, "layer_cases_tn_variants.npz"), **blob)
+    print("layer_cases_tn_variants.npz", os.path.getsize(os.path.join(OUT, "layer_cases_tn_variants.npz")) >> 10, "KiB")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "letterbox":
         gen_letterbox()
+    elif len(sys.argv) > 1 and sys.argv[1] == "variants":
+        gen_variants()
     else:
         main()
         gen_letterbox()
+        gen_variants()

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Per-layer device times (CUDA events inside the library) of one full YOLOv2-416 COCO INT16 pass,
+"""Per-layer device times (CUDA events inside the library) of one full YOLOv2 pass (default 416 COCO INT16; Y2_SIZE / Y2_CLASSES / Y2_TN),
 with each kernel's roofline: exact round-and-saturate steps/s (and the int8-OP equivalent) for conv,
 algorithmic GB/s for the bandwidth kernels.  Usage: python profiles/layer_table.py [batch] [precision]"""
 import json
@@ -17,7 +17,9 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 precision = sys.argv[2] if len(sys.argv) > 2 else "int16"
 eb = 2 if precision == "int16" else 4
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
-net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 80))
+size = int(os.environ.get("Y2_SIZE", "416"))        # BASELINE configs: 416 (COCO / VOC), 608 (COCO)
+classes = int(os.environ.get("Y2_CLASSES", "80"))   # 80 = COCO, 20 = VOC
+net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(size, size, classes))
 tn = int(os.environ.get("Y2_TN", "4"))          # emulate a reference built with --tn <Y2_TN> (yolo2cuda_set_tile_params)
 pack = yw.synth_pack(net, precision, seed=0, tn=tn)
 from yolo2_b200.accel import Accelerator  # noqa: E402
@@ -50,4 +52,4 @@ for i, (l, t) in enumerate(zip(net.layers, ms)):
         r["GBps"] = by / (t * 1e-3) / 1e9
         r["frac_of_hbm_peak"] = r["GBps"] / peaks["hbm_gbs"]
     rows.append(r)
-print(json.dumps({"batch": batch, "precision": precision, "tn": tn, "total_ms": tot, "fps": batch / (tot * 1e-3), "layers": rows}, indent=1))
+print(json.dumps({"batch": batch, "precision": precision, "tn": tn, "size": size, "classes": classes, "total_ms": tot, "fps": batch / (tot * 1e-3), "layers": rows}, indent=1))

@@ -91,3 +91,17 @@ def test_letterbox_golden(i, oracle):
     nw, nh = (int(v) for v in g[f"lb_{i}_net"])
     got = oracle.letterbox_u8(g[f"lb_{i}_img"], nw, nh)
     assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), g[f"lb_{i}_out"].view(np.uint32))
+
+
+# ---- rounding-group variants: outputs of the reference BUILT with --tn 8 / 32, frozen in layer_cases_tn_variants.npz ----
+
+@pytest.mark.parametrize("i", range(5))
+def test_conv_int16_tn_variant_golden(i, oracle):
+    g = np.load(os.path.join(GOLD, "layer_cases_tn_variants.npz"))
+    a = _args(g[f"v_{i}_args"])
+    q = [int(v) for v in g[f"v_{i}_q"]]
+    assert a["TN"] == min(int(g[f"v_{i}_tn"][0]), a["IFM_num"])
+    got = oracle.conv(g[f"v_{i}_x"], g[f"v_{i}_w"], g[f"v_{i}_b"], a["IFM_num"], a["OFM_num"], a["Ksize"], a["Kstride"], a["Input_w"],
+                      a["Input_h"], a["Output_w"], a["Output_h"], a["Padding"], a["IsNL"], a["TM"], a["TN"], *q)
+    ow = a["Output_w"]
+    assert np.array_equal(got[..., :ow], g[f"v_{i}_out"][..., :ow])

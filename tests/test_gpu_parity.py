@@ -484,3 +484,22 @@ def test_whole_net_rounding_group_variant(tn, oracle):
         oracle.set_tile_params(4, 32)
         y.close()
         acc.close()
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_tn_variant_golden_gpu(i):
+    """the CUDA path (generic kernel for Tn = 8, tcgen05 kernel for Tn = 32) against outputs of the reference built with that Tn"""
+    from oracle.gen_golden import ARG_KEYS
+    from yolo2_b200.accel import Accelerator
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layer_cases_tn_variants.npz"))
+    a = dict(zip(ARG_KEYS, [int(v) for v in g[f"v_{i}_args"]]))
+    tn = int(g[f"v_{i}_tn"][0])
+    acc = Accelerator(0, "int16")
+    try:
+        acc.set_tile_params(tn, 32)
+        got = accel_call(acc, a, g[f"v_{i}_x"], g[f"v_{i}_w"], g[f"v_{i}_b"], [int(v) for v in g[f"v_{i}_q"]])
+        assert np.array_equal(valid(got, a["Output_w"]), valid(g[f"v_{i}_out"], a["Output_w"])), acc.last_kernel
+        if tn == 32:
+            assert acc.last_kernel.startswith("conv_i16_tc32<")
+    finally:
+        acc.close()
