@@ -37,6 +37,7 @@ def build(ref=True, quiet=True):
     subprocess.check_call(["make", "-C", HERE, "oracle"], stdout=out)
     if ref and os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-C", HERE, "ref"], stdout=out)
+        subprocess.check_call(["make", "-C", HERE, "ref-variants"], stdout=out)   # the reference built with --tn 8 / 16 / 32
 
 
 def ref_so(precision="int16", tn=4):
