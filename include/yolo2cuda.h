@@ -56,12 +56,13 @@ typedef struct yolo2cuda_net yolo2cuda_net;   /* one loaded network: plan, weigh
 /* Creates a context on CUDA device `device` for `precision` (16 or 32). */
 int yolo2cuda_create(yolo2cuda_ctx **ctx, int device, int precision);
 int yolo2cuda_destroy(yolo2cuda_ctx *ctx);
-/* Launch all work of this context on `cuda_stream` (a cudaStream_t; NULL = the context's own). */
 /* Tile parameters of the reference BUILD this context emulates (scripts/hw_params_gen.py --tn/--tm ->
  * hls/core/params.hpp): Tn = input-channel tile = the ROUNDING GROUP of the int16 accumulator
  * (core_scheduler.cpp:45, core_compute.cpp:65-120), Tm = output-channel weight block.  Defaults 4 / 32 (the
  * reference's); results are bit-exact to a reference compiled with the same values.  Set before net_create. */
 int yolo2cuda_set_tile_params(yolo2cuda_ctx *ctx, int Tn, int Tm);
+/* Launch all work of this context on `cuda_stream` (a cudaStream_t).  NULL = back to the context's own non-blocking stream;
+ * the legacy default stream (handle 0 in most frameworks) is addressed as cudaStreamLegacy, i.e. (void *)1. */
 int yolo2cuda_set_stream(yolo2cuda_ctx *ctx, void *cuda_stream);
 int yolo2cuda_synchronize(yolo2cuda_ctx *ctx);
 /* Text of the last error on this context (never NULL). */
@@ -175,6 +176,15 @@ int yolo2cuda_net_layer_times(yolo2cuda_net *net, float *ms, int n_layers);
 int yolo2cuda_region_detections(const float *region, int lw, int lh, int n, int classes,
                                 const float *anchors, int im_w, int im_h, int net_w, int net_h,
                                 float thresh, float nms, float *boxes, float *probs, float *objectness);
+
+/* The same on the GPU for a batch of region tensors that are still on the device: DEVICE pointers,
+ * async on the stream.  region: float [batch][n*(5+classes)*lw*lh]; outputs per frame boxes [lw*lh*n][4], probs
+ * [lw*lh*n][classes], objectness [lw*lh*n].  POSITIONAL: entry cell*n + anchor (the order in which the reference fills its
+ * candidate list); entries at or below the objectness threshold are zero.  The reference's list is compacted and re-ordered by
+ * qsort; the SET of surviving (box, class, probability) is bit-identical.  lw*lh*n <= 1024. */
+int yolo2cuda_region_detections_dev(yolo2cuda_ctx *ctx, const float *region, int batch, int lw, int lh, int n, int classes,
+                                    const float *anchors_host, int im_w, int im_h, int net_w, int net_h,
+                                    float thresh, float nms, float *boxes, float *probs, float *objectness);
 
 #ifdef __cplusplus
 }

@@ -503,3 +503,40 @@ def test_tn_variant_golden_gpu(i):
             assert acc.last_kernel.startswith("conv_i16_tc32<")
     finally:
         acc.close()
+
+
+# ---- boxes + per-class NMS on the GPU --------------------------------------------------------------------------
+
+def _det_set(boxes, probs):
+    """order-free view of a detection result: sorted rows (class, prob bits, box bits) of every non-zero probability"""
+    rows = []
+    for b, p in zip(boxes, probs):
+        for k in np.nonzero(p)[0]:
+            rows.append((int(k), int(np.float32(p[k]).view(np.uint32)), *[int(v) for v in np.asarray(b, np.float32).view(np.uint32)]))
+    return sorted(rows)
+
+
+@pytest.mark.parametrize("im_w,im_h,thresh", [(640, 480, 0.25), (333, 500, 0.1), (416, 416, 0.24)])
+def test_gpu_detections_equal_reference_set(im_w, im_h, thresh, accel16, oracle):
+    """detect_kernel (csrc/bw_ops.cu) against the oracle's get_region_detections + correct_region_boxes + do_nms_sort: the same
+    surviving (class, probability, box) tuples, bit for bit (incl. the box w/h through the restated glibc expf), for a batch."""
+    import torch
+    from yolo2_b200.model import region_detections_gpu
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 80))
+    l = net.layers[-1]
+    rng = np.random.default_rng(im_w + im_h)
+    B = 3
+    raw = rng.normal(0, 1.5, (B, l.n, 5 + l.classes, l.h, l.w)).astype(np.float32)
+    raw[:, :, 4] = rng.normal(-2.0, 2.0, (B, l.n, l.h, l.w))          # a few dozen cells above the objectness threshold
+    raw[:, :, 5] += 3.0                                                  # one popular class: real suppression work in its NMS
+    region = np.stack([oracle.region_forward(r.reshape(-1), l.w, l.h, l.n, l.classes) for r in raw])
+    gb, gp, go = region_detections_gpu(accel16, net, torch.from_numpy(region).cuda(), im_w, im_h, thresh, 0.45)
+    gb, gp, go = gb.cpu().numpy(), gp.cpu().numpy(), go.cpu().numpy()
+    kept = 0
+    for f in range(B):
+        wb, wp, wo = oracle.region_boxes_nms(region[f], l.w, l.h, l.n, l.classes, l.anchors, im_w, im_h, net.w, net.h, thresh, 0.45)
+        want, got = _det_set(wb, wp), _det_set(gb[f], gp[f])
+        assert got == want
+        assert sorted(np.float32(wo[wo != 0]).view(np.uint32).tolist()) == sorted(go[f][go[f] != 0].view(np.uint32).tolist())
+        kept += len(want)
+    assert kept > 20        # the case is not vacuous

@@ -127,3 +127,27 @@ def test_host_detections_match_oracle(oracle):
                                         for x, q, z in zip(bb, pp, oo))
         assert len(b) == live.sum() > 10
         assert key(b, p, o) == key(wb[live], wp[live], wo[live])
+
+
+def test_glibc_expf_restatement_matches_libm(tmp_path):
+    """oracle/expf_check.c: the double-arithmetic restatement of glibc's expf that the CUDA detection kernel uses for the box
+    width / height equals the host libm's expf (what the reference's std::exp(float) calls) on 2^22 inputs, bit for bit."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(tmp_path, "expf_check")
+    subprocess.check_call(["gcc", "-O2", "-fno-builtin", "-ffp-contract=off", "-o", exe, os.path.join(root, "oracle", "expf_check.c"), "-lm"])
+    assert subprocess.check_output([exe]).decode().strip() == "0"
+
+
+def test_detections_jsonl_format():
+    """the board application's JSONL record (linux_app/src/main.c:1028-1075): best class per box, normalised box, pixel corners"""
+    import json
+    import numpy as np
+    from yolo2_b200.model import detections_jsonl
+    boxes = np.array([[0.5, 0.5, 0.2, 0.4], [0.1, 0.1, 0.05, 0.05]], np.float32)
+    probs = np.array([[0.0, 0.9, 0.3], [0.1, 0.0, 0.0]], np.float32)
+    rec = json.loads(detections_jsonl(boxes, probs, 640, 480, labels=["a", "b", "c"], thresh=0.25, source="cam0", frame_index=7))
+    assert rec["width"] == 640 and rec["frame_index"] == 7 and len(rec["detections"]) == 1
+    d = rec["detections"][0]
+    assert d["class_id"] == 1 and d["label"] == "b" and abs(d["prob"] - 0.9) < 1e-5
+    assert d["bbox_px"] == {"x0": int((0.5 - 0.1) * 640), "y0": int((0.5 - 0.2) * 480), "x1": int((0.5 + 0.1) * 640), "y1": int((0.5 + 0.2) * 480)}

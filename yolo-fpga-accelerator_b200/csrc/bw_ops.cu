@@ -474,4 +474,153 @@ void launch_letterbox(const unsigned char *src, float *dst, int B, int iw, int i
     letterbox_kernel<<<blocks_for(total, 256), 256, 0, st>>>(src, dst, B, p);
 }
 
+// ---- detections on the GPU: get_region_detections + correct_region_boxes + do_nms_sort -------------------------------------
+// (src/core/yolo_region.cpp:15-53,169-195, src/core/yolo_post.cpp:22-85).  One CTA = one (class, frame).  Every float operation of the
+// reference is one rounded operation here; the box w/h use glibc's expf ALGORITHM restated in double arithmetic (table of 2^(i/32) +
+// cubic, sysdeps/ieee754/flt-32/e_expf.c of glibc >= 2.27): it reproduces the host's expf bit for bit (checked against libm on 2^25
+// inputs, oracle/expf_check.c), which CUDA's own expf (2 ulp) does not.  Output is POSITIONAL (entry e = cell*n + anchor, the order in
+// which the reference fills its candidate list; entries at or below the objectness threshold are all-zero) instead of the
+// reference's compacted list whose final order depends on qsort; the set of surviving (box, class, probability) is identical.  Equal
+// probabilities inside one class are ordered by entry index (the stable order glibc's merge-sort qsort produces).
+struct DetParams {
+    int lw, lh, n, classes, im_w, im_h, net_w, net_h, new_w, new_h;
+    float thresh, nms;
+    float anchors[32];
+    double expf_tab[32];       // 2^(i/32), correctly rounded
+};
+
+__device__ __forceinline__ float glibc_expf(float x, const double *tab)
+{
+    const double InvLn2N = 0x1.71547652b82fep+0 * 32, SHIFT = 0x1.8p+52;
+    const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32, C2 = 0x1.62e42ff0c52d6p-1 / 32;
+    const double xd = (double)x;
+    const double z = __dmul_rn(InvLn2N, xd);
+    double kd = __dadd_rn(z, SHIFT);
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd = __dadd_rn(kd, -SHIFT);
+    const double r = __dadd_rn(z, -kd);
+    unsigned long long t = (unsigned long long)__double_as_longlong(tab[ki % 32]) - ((ki % 32) << 47);
+    t += ki << 47;
+    const double s = __longlong_as_double((long long)t);
+    const double zz = __dadd_rn(__dmul_rn(C0, r), C1);
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(C2, r), 1.0);
+    y = __dadd_rn(__dmul_rn(zz, r2), y);
+    y = __dmul_rn(y, s);
+    return __double2float_rn(y);
+}
+
+__device__ __forceinline__ float det_overlap(float x1, float w1, float x2, float w2)
+{
+    const float l1 = __fsub_rn(x1, __fdiv_rn(w1, 2.f)), l2 = __fsub_rn(x2, __fdiv_rn(w2, 2.f));
+    const float left = l1 > l2 ? l1 : l2;
+    const float r1 = __fadd_rn(x1, __fdiv_rn(w1, 2.f)), r2 = __fadd_rn(x2, __fdiv_rn(w2, 2.f));
+    const float right = r1 < r2 ? r1 : r2;
+    return __fsub_rn(right, left);
+}
+__device__ __forceinline__ float det_iou(float4 a, float4 b)   // box = (x, y, w, h)
+{
+    const float w = det_overlap(a.x, a.z, b.x, b.z), h = det_overlap(a.y, a.w, b.y, b.w);
+    const float inter = (w < 0 || h < 0) ? 0.f : __fmul_rn(w, h);
+    const float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.z, a.w), __fmul_rn(b.z, b.w)), inter);
+    return __fdiv_rn(inter, uni);
+}
+
+constexpr int kDetMax = 1024;   // candidates per frame the kernel can hold (13 x 13 x 5 = 845 for YOLOv2-416, 19 x 19 x 5 > 1024 -> host path)
+
+__global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ region, float *__restrict__ boxes, float *__restrict__ probs,
+                                                      float *__restrict__ objectness, const DetParams p)
+{
+    __shared__ float4 s_box[kDetMax];
+    __shared__ float s_p[kDetMax];
+    __shared__ short s_src[kDetMax];     // sorted position -> entry
+    __shared__ float4 s_sbox[kDetMax];
+    __shared__ float s_sp[kDetMax];
+    __shared__ int s_m;
+    const int k = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const int wh = p.lw * p.lh, total = wh * p.n, per = 5 + p.classes;
+    const float *reg = region + (size_t)f * p.n * per * wh;
+    float *bo = boxes + (size_t)f * total * 4, *po = probs + (size_t)f * total * p.classes, *oo = objectness + (size_t)f * total;
+    if (tid == 0) s_m = 0;
+    // decode (get_region_detections + correct_region_boxes), entry e = cell * n + anchor
+    for (int e = tid; e < total; e += blockDim.x) {
+        const int cell = e / p.n, a = e - cell * p.n;
+        const int row = cell / p.lw, col = cell - row * p.lw;
+        const float *x = reg + (size_t)a * per * wh + cell;
+        const float obj = x[(size_t)4 * wh];
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        float pr = 0.f, o = 0.f;
+        if (obj > p.thresh) {
+            o = obj;
+            b.x = __fdiv_rn(__fadd_rn((float)col, x[0]), (float)p.lw);
+            b.y = __fdiv_rn(__fadd_rn((float)row, x[(size_t)wh]), (float)p.lh);
+            b.z = __fdiv_rn(__fmul_rn(glibc_expf(x[(size_t)2 * wh], p.expf_tab), p.anchors[2 * a]), (float)p.lw);
+            b.w = __fdiv_rn(__fmul_rn(glibc_expf(x[(size_t)3 * wh], p.expf_tab), p.anchors[2 * a + 1]), (float)p.lh);
+            // correct_region_boxes, relative = 1 (double where the reference's expression is double)
+            b.x = __double2float_rn(__ddiv_rn(__dsub_rn((double)b.x, __ddiv_rn(__ddiv_rn((double)(p.net_w - p.new_w), 2.), (double)p.net_w)),
+                                              (double)__fdiv_rn((float)p.new_w, (float)p.net_w)));
+            b.y = __double2float_rn(__ddiv_rn(__dsub_rn((double)b.y, __ddiv_rn(__ddiv_rn((double)(p.net_h - p.new_h), 2.), (double)p.net_h)),
+                                              (double)__fdiv_rn((float)p.new_h, (float)p.net_h)));
+            b.z = __fmul_rn(b.z, __fdiv_rn((float)p.net_w, (float)p.new_w));
+            b.w = __fmul_rn(b.w, __fdiv_rn((float)p.net_h, (float)p.new_h));
+            const float q = __fmul_rn(obj, x[(size_t)(5 + k) * wh]);
+            pr = q > p.thresh ? q : 0.f;
+        }
+        s_box[e] = b;
+        s_p[e] = pr;
+        if (k == 0) {
+            reinterpret_cast<float4 *>(bo)[e] = b;
+            oo[e] = o;
+        }
+    }
+    __syncthreads();
+    if (p.nms > 0.f) {
+        // do_nms_sort for class k: order the entries with a non-zero probability by probability (descending, entry index breaks ties) ...
+        for (int e = tid; e < total; e += blockDim.x) {
+            const float pe = s_p[e];
+            if (pe == 0.f) continue;
+            int rank = 0;
+            for (int j = 0; j < total; ++j) {
+                const float pj = s_p[j];
+                rank += (pj > pe) || (pj == pe && j < e);
+            }
+            s_src[rank] = (short)e;
+            s_sbox[rank] = s_box[e];
+            s_sp[rank] = pe;
+            atomicAdd(&s_m, 1);
+        }
+        __syncthreads();
+        const int m = s_m;
+        // ... then every surviving entry suppresses the later ones it overlaps
+        for (int i = 0; i < m; ++i) {
+            if (s_sp[i] != 0.f) {
+                const float4 a = s_sbox[i];
+                for (int j = i + 1 + tid; j < m; j += blockDim.x)
+                    if (det_iou(a, s_sbox[j]) > p.nms) s_sp[j] = 0.f;
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < m; i += blockDim.x) s_p[s_src[i]] = s_sp[i];
+        __syncthreads();
+    }
+    for (int e = tid; e < total; e += blockDim.x) po[(size_t)e * p.classes + k] = s_p[e];
+}
+
+// returns 0 when launched, -1 when the frame has more candidates than the kernel holds
+int launch_detect(const float *region, float *boxes, float *probs, float *objectness, int B, int lw, int lh, int n, int classes,
+                  const float *anchors, int im_w, int im_h, int net_w, int net_h, float thresh, float nms, const double *expf_tab,
+                  cudaStream_t st)
+{
+    if (lw * lh * n > kDetMax || n > 16) return -1;
+    DetParams p;
+    p.lw = lw; p.lh = lh; p.n = n; p.classes = classes; p.im_w = im_w; p.im_h = im_h; p.net_w = net_w; p.net_h = net_h;
+    if (((float)net_w / im_w) < ((float)net_h / im_h)) { p.new_w = net_w; p.new_h = (im_h * net_w) / im_w; }   // correct_region_boxes :31-37
+    else { p.new_h = net_h; p.new_w = (im_w * net_h) / im_h; }
+    p.thresh = thresh; p.nms = nms;
+    for (int i = 0; i < 2 * n; ++i) p.anchors[i] = anchors[i];
+    for (int i = 0; i < 32; ++i) p.expf_tab[i] = expf_tab[i];
+    detect_kernel<<<dim3(classes, B), 256, 0, st>>>(region, boxes, probs, objectness, p);
+    return 0;
+}
+
 }  // namespace y2

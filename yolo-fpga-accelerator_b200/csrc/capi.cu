@@ -3,6 +3,7 @@
 // yolov2_hls_ps (hls/models/yolov2/yolo2_model.cpp:229-449).  No CPU fallback anywhere: every
 // compute entry needs a CUDA device and fails with a YOLO2CUDA_* code otherwise.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -371,6 +372,29 @@ int yolo2cuda_region_dev(yolo2cuda_ctx *ctx, const void *in, float *out, int w, 
     if (w <= 0 || h <= 0 || n <= 0 || classes <= 0 || coords < 4) return fail(ctx, YOLO2CUDA_ERROR, "bad region dims");
     CUDA_OK(ctx, cudaSetDevice(ctx->device));
     launch_region(in, out, 1, w, h, n, classes, coords, softmax, background, q, 0, 0, ctx->elem, ctx->stream);
+    ctx->launches += 1;
+    CUDA_OK(ctx, cudaGetLastError());
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_region_detections_dev(yolo2cuda_ctx *ctx, const float *region, int batch, int lw, int lh, int n, int classes,
+                                    const float *anchors_host, int im_w, int im_h, int net_w, int net_h, float thresh, float nms,
+                                    float *boxes, float *probs, float *objectness)
+{
+    if (!ctx || !region || !anchors_host || !boxes || !probs || !objectness) return YOLO2CUDA_ERROR;
+    if (batch <= 0 || lw <= 0 || lh <= 0 || n <= 0 || classes <= 0 || im_w <= 0 || im_h <= 0 || net_w <= 0 || net_h <= 0)
+        return fail(ctx, YOLO2CUDA_ERROR, "region_detections_dev: bad dimensions");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    // 2^(i/32) correctly rounded: the table of glibc's expf (long double exp2, then one rounding to double)
+    static double tab[32];
+    static bool tab_ready = false;
+    if (!tab_ready) {
+        for (int i = 0; i < 32; ++i) tab[i] = (double)exp2l((long double)i / 32);
+        tab_ready = true;
+    }
+    if (launch_detect(region, boxes, probs, objectness, batch, lw, lh, n, classes, anchors_host, im_w, im_h, net_w, net_h, thresh, nms,
+                      tab, ctx->stream) < 0)
+        return fail(ctx, YOLO2CUDA_ERROR, "region_detections_dev: more than 1024 candidates per frame (use yolo2cuda_region_detections)");
     ctx->launches += 1;
     CUDA_OK(ctx, cudaGetLastError());
     return YOLO2CUDA_SUCCESS;

@@ -94,6 +94,10 @@ void launch_quantize(const float *in, int16_t *out, size_t count, int q_in, cuda
 // frames float [B][C][H][W] -> C4 (quantised when elem_bytes==2)
 void launch_frames_to_c4(const float *frames, void *dst, int B, int C, int H, int W, long long dst_frame_stride,
                          int q_in, int elem_bytes, cudaStream_t st);
+// boxes + per-class NMS on the GPU (yolo_region.cpp:15-53,169-195, yolo_post.cpp:22-85); positional output, see bw_ops.cu
+int launch_detect(const float *region, float *boxes, float *probs, float *objectness, int B, int lw, int lh, int n, int classes,
+                  const float *anchors, int im_w, int im_h, int net_w, int net_h, float thresh, float nms, const double *expf_tab,
+                  cudaStream_t st);
 // stb u8 [B][ih][iw][ic] -> float [B][ic][net_h][net_w], darknet letterbox (yolo_image.cpp:84-165,178-187), bit-exact
 void launch_letterbox(const unsigned char *src, float *dst, int B, int iw, int ih, int ic, int net_w, int net_h, cudaStream_t st);
 void launch_reorg_driver_planar(const void *in, void *out, int c, int h, int w, int shift, int elem_bytes, cudaStream_t st);

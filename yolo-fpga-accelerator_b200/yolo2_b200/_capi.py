@@ -63,6 +63,8 @@ SYMBOLS = {
     "yolo2cuda_net_layer_times": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "yolo2cuda_region_detections": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] + [C.c_int] * 4 +
                                     [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yolo2cuda_region_detections_dev": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p] + [C.c_int] * 4 +
+                                        [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

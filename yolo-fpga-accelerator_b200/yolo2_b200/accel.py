@@ -40,6 +40,12 @@ class Accelerator:
         _capi.check(self.ctx, self.lib.yolo2cuda_set_tile_params(self.ctx, tn, tm))
         self.tn, self.tm = tn, tm
 
+    def use_torch_stream(self, device=None):
+        """Launch on torch's current stream.  torch's default stream has handle 0, which yolo2cuda_set_stream reads as "back to
+        the context's own (non-blocking) stream"; the legacy default stream is addressed by CUDA's cudaStreamLegacy handle (1)."""
+        import torch
+        self.set_stream(torch.cuda.current_stream(device).cuda_stream or 1)
+
     def set_stream(self, cuda_stream_ptr):
         _capi.check(self.ctx, self.lib.yolo2cuda_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr)))
 
@@ -98,7 +104,7 @@ def letterbox_image(acc: "Accelerator", images, net_w: int, net_h: int):
     assert images.is_cuda and images.dtype == torch.uint8 and images.dim() == 4 and images.is_contiguous()
     b, ih, iw, ic = images.shape
     out = torch.empty((b, ic, net_h, net_w), dtype=torch.float32, device=images.device)
-    acc.set_stream(torch.cuda.current_stream(images.device).cuda_stream)
+    acc.use_torch_stream(images.device)
     _capi.check(acc.ctx, acc.lib.yolo2cuda_letterbox_dev(acc.ctx, C.c_void_p(images.data_ptr()), b, iw, ih, ic, C.c_void_p(out.data_ptr()), net_w, net_h))
     return out
 

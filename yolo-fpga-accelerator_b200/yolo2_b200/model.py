@@ -137,6 +137,47 @@ def region_detections(net: _cfg.Network, region: np.ndarray, im_w: int, im_h: in
     return boxes[:k], probs[:k], obj[:k]
 
 
+def region_detections_gpu(acc: Accelerator, net: _cfg.Network, region, im_w: int, im_h: int, thresh=0.25, nms=0.45):
+    """Boxes + per-class NMS on the GPU for a batch (yolo2cuda_region_detections_dev).  region: torch.float32 CUDA tensor
+    [batch][...] (what forward_ptr(..., device=True) leaves on the device).  Returns CUDA tensors boxes [batch][total][4],
+    probs [batch][total][classes], objectness [batch][total]; POSITIONAL (entry cell*n + anchor), zero rows for rejected cells."""
+    import torch
+    l = net.layers[-1]
+    total = l.w * l.h * l.n
+    region = region.contiguous().view(region.shape[0], -1)
+    B = region.shape[0]
+    boxes = torch.empty((B, total, 4), dtype=torch.float32, device=region.device)
+    probs = torch.empty((B, total, l.classes), dtype=torch.float32, device=region.device)
+    obj = torch.empty((B, total), dtype=torch.float32, device=region.device)
+    anchors = np.asarray(l.anchors, np.float32)
+    acc.use_torch_stream(region.device)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _capi.check(acc.ctx, acc.lib.yolo2cuda_region_detections_dev(acc.ctx, p(region), B, l.w, l.h, l.n, l.classes,
+                                                                 anchors.ctypes.data_as(C.c_void_p), im_w, im_h, net.w, net.h,
+                                                                 C.c_float(thresh), C.c_float(nms), p(boxes), p(probs), p(obj)))
+    return boxes, probs, obj
+
+
+def detections_jsonl(boxes: np.ndarray, probs: np.ndarray, width: int, height: int, labels=None, thresh: float = 0.25,
+                     source: str = "", frame_index: int = 0, mode: str = "image") -> str:
+    """One JSONL record per inference in the format of the reference's board application
+    (linux_app/src/main.c:1028-1075): best class per box, normalised box and pixel corners."""
+    import json
+    dets = []
+    for b, pr in zip(np.asarray(boxes), np.asarray(probs)):
+        c = int(np.argmax(pr))
+        best = float(pr[c])
+        if not best > thresh:
+            continue
+        x, y, w, h = (float(v) for v in b)
+        dets.append({"class_id": c, "label": (labels[c] if labels is not None and c < len(labels) else "unknown"),
+                     "prob": round(best, 6), "bbox_norm": {"x": round(x, 6), "y": round(y, 6), "w": round(w, 6), "h": round(h, 6)},
+                     "bbox_px": {"x0": int((x - w * 0.5) * width), "y0": int((y - h * 0.5) * height),
+                                 "x1": int((x + w * 0.5) * width), "y1": int((y + h * 0.5) * height)}})
+    return json.dumps({"mode": mode, "source": source, "frame_index": frame_index, "inference_index": frame_index,
+                       "width": width, "height": height, "detections": dets}, separators=(",", ":"))
+
+
 def yolov2_cuda_ps(net: _cfg.Network, input: np.ndarray, pack: WeightsPack, device: int = 0) -> np.ndarray:
     """Single-frame mirror of yolov2_hls_ps(net, input, precision): returns layers[n-1].output."""
     y = Yolo2Net(net, pack, device=device, max_batch=1)
