@@ -150,4 +150,7 @@ def test_detections_jsonl_format():
     assert rec["width"] == 640 and rec["frame_index"] == 7 and len(rec["detections"]) == 1
     d = rec["detections"][0]
     assert d["class_id"] == 1 and d["label"] == "b" and abs(d["prob"] - 0.9) < 1e-5
-    assert d["bbox_px"] == {"x0": int((0.5 - 0.1) * 640), "y0": int((0.5 - 0.2) * 480), "x1": int((0.5 + 0.1) * 640), "y1": int((0.5 + 0.2) * 480)}
+    f = np.float32      # (int)((b.x - b.w * 0.5f) * (float)frame_w) in float arithmetic, linux_app/src/main.c:1054-1057
+    assert d["bbox_px"] == {"x0": int((f(0.5) - f(0.2) * f(0.5)) * f(640)), "y0": int((f(0.5) - f(0.4) * f(0.5)) * f(480)),
+                            "x1": int((f(0.5) + f(0.2) * f(0.5)) * f(640)), "y1": int((f(0.5) + f(0.4) * f(0.5)) * f(480))}
+    assert d["bbox_px"]["x0"] == 256

@@ -478,7 +478,7 @@ void launch_letterbox(const unsigned char *src, float *dst, int B, int iw, int i
 // (src/core/yolo_region.cpp:15-53,169-195, src/core/yolo_post.cpp:22-85).  One CTA = one (class, frame).  Every float operation of the
 // reference is one rounded operation here; the box w/h use glibc's expf ALGORITHM restated in double arithmetic (table of 2^(i/32) +
 // cubic, sysdeps/ieee754/flt-32/e_expf.c of glibc >= 2.27): it reproduces the host's expf bit for bit (checked against libm on 2^25
-// inputs, oracle/expf_check.c), which CUDA's own expf (2 ulp) does not.  Output is POSITIONAL (entry e = cell*n + anchor, the order in
+// inputs by the checker program expf_check.c of the test tree), which CUDA's own expf (2 ulp) does not.  Output is POSITIONAL (entry e = cell*n + anchor, the order in
 // which the reference fills its candidate list; entries at or below the objectness threshold are all-zero) instead of the
 // reference's compacted list whose final order depends on qsort; the set of surviving (box, class, probability) is identical.  Equal
 // probabilities inside one class are ordered by entry index (the stable order glibc's merge-sort qsort produces).

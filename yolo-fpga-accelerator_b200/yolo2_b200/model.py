@@ -169,11 +169,13 @@ def detections_jsonl(boxes: np.ndarray, probs: np.ndarray, width: int, height: i
         best = float(pr[c])
         if not best > thresh:
             continue
-        x, y, w, h = (float(v) for v in b)
+        x, y, w, h = (np.float32(v) for v in b)            # the pixel corners are float32 arithmetic in the reference
+        half, fw, fh = np.float32(0.5), np.float32(width), np.float32(height)
         dets.append({"class_id": c, "label": (labels[c] if labels is not None and c < len(labels) else "unknown"),
-                     "prob": round(best, 6), "bbox_norm": {"x": round(x, 6), "y": round(y, 6), "w": round(w, 6), "h": round(h, 6)},
-                     "bbox_px": {"x0": int((x - w * 0.5) * width), "y0": int((y - h * 0.5) * height),
-                                 "x1": int((x + w * 0.5) * width), "y1": int((y + h * 0.5) * height)}})
+                     "prob": round(best, 6),
+                     "bbox_norm": {"x": round(float(x), 6), "y": round(float(y), 6), "w": round(float(w), 6), "h": round(float(h), 6)},
+                     "bbox_px": {"x0": int((x - w * half) * fw), "y0": int((y - h * half) * fh),
+                                 "x1": int((x + w * half) * fw), "y1": int((y + h * half) * fh)}})
     return json.dumps({"mode": mode, "source": source, "frame_index": frame_index, "inference_index": frame_index,
                        "width": width, "height": height, "detections": dets}, separators=(",", ":"))
 
