@@ -122,6 +122,27 @@ __global__ void maxpool_c4_kernel(const T *__restrict__ in, T *__restrict__ out,
         *reinterpret_cast<typename Vec4<T>::type *>(best);
 }
 
+// The network's five pools (2x2, stride 2, even dims, int16): the two window pixels of a row are one aligned 16-byte word, so a
+// thread does two LDG.128 and one STG.64 and a warp reads 512 contiguous bytes per row.
+__device__ __forceinline__ unsigned vmax_s16x2(unsigned a, unsigned b) { return __vmaxs2(a, b); }
+__global__ void maxpool_c4_i16_s2_kernel(const int16_t *__restrict__ in, int16_t *__restrict__ out, long long total, int G, int iw, int ih,
+                                         int ow, int oh, long long ifs, long long ofs)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int x = idx % ow;
+    long long r = idx / ow;
+    int y = r % oh; r /= oh;
+    int g = r % G;
+    long long f = r / G;
+    const int16_t *src = in + f * ifs + (((long long)g * ih + 2 * y) * iw + 2 * x) * 4;
+    const uint4 a = *reinterpret_cast<const uint4 *>(src), b = *reinterpret_cast<const uint4 *>(src + (long long)iw * 4);
+    uint2 m;
+    m.x = vmax_s16x2(vmax_s16x2(a.x, a.z), vmax_s16x2(b.x, b.z));
+    m.y = vmax_s16x2(vmax_s16x2(a.y, a.w), vmax_s16x2(b.y, b.w));
+    *reinterpret_cast<uint2 *>(out + f * ofs + (((long long)g * oh + y) * ow + x) * 4) = m;
+}
+
 // LayerType 2: out[m+2ky+kx][y][x] = in[m][2y+ky][2x+kx] for m stepping by TM (core_compute.cpp:354-379,
 // core_scheduler.cpp:88-112, yolo2_accel.cpp:127-169).
 template <typename T>
@@ -342,7 +363,10 @@ void launch_maxpool_c4(const void *in, void *out, int B, int G, int kstride, int
                        long long ifs, long long ofs, int elem_bytes, cudaStream_t st)
 {
     long long total = (long long)B * G * oh * ow;
-    if (elem_bytes == 2)
+    if (elem_bytes == 2 && kstride == 2 && iw % 2 == 0 && ih % 2 == 0 && ow == iw / 2 && oh == ih / 2 && ifs % 8 == 0 &&
+        ((uintptr_t)in & 15) == 0)
+        maxpool_c4_i16_s2_kernel<<<blocks_for(total, 256), 256, 0, st>>>((const int16_t *)in, (int16_t *)out, total, G, iw, ih, ow, oh, ifs, ofs);
+    else if (elem_bytes == 2)
         maxpool_c4_kernel<int16_t><<<blocks_for(total, 256), 256, 0, st>>>((const int16_t *)in, (int16_t *)out, B, G, kstride, iw, ih, ow, oh, ifs, ofs);
     else
         maxpool_c4_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>((const float *)in, (float *)out, B, G, kstride, iw, ih, ow, oh, ifs, ofs);
