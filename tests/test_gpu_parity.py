@@ -540,3 +540,25 @@ def test_gpu_detections_equal_reference_set(im_w, im_h, thresh, accel16, oracle)
         assert sorted(np.float32(wo[wo != 0]).view(np.uint32).tolist()) == sorted(go[f][go[f] != 0].view(np.uint32).tolist())
         kept += len(want)
     assert kept > 20        # the case is not vacuous
+
+
+def test_detection_stream_end_to_end(oracle):
+    """yolo2_b200.app.DetectionStream (u8 frames -> letterbox -> network -> boxes + NMS, all on the GPU) against the same chain through
+    the oracle: letterbox_u8, net_forward, region_boxes_nms - identical detection sets, and well-formed JSONL records."""
+    import json
+    from yolo2_b200.app import DetectionStream
+    net, pack = _net_case(416, 416, 3, 8, "default", seed=5)
+    imgs = np.random.default_rng(123).integers(0, 256, (3, 120, 160, 3), dtype=np.uint8)
+    ds = DetectionStream(net, pack, batch=4, thresh=0.05, nms=0.45)
+    try:
+        boxes, probs, obj = ds.detect(imgs)
+        lines = ds.detect_jsonl(imgs, labels=["a", "b", "c"], source="test")
+    finally:
+        ds.close()
+    l = net.layers[-1]
+    for f in range(3):
+        region, _ = oracle.net_forward(net, oracle.letterbox_u8(imgs[f], 416, 416), pack)
+        wb, wp, wo = oracle.region_boxes_nms(region, l.w, l.h, l.n, l.classes, l.anchors, 160, 120, net.w, net.h, 0.05, 0.45)
+        assert _det_set(boxes[f], probs[f]) == _det_set(wb, wp)
+        rec = json.loads(lines[f])
+        assert rec["width"] == 160 and rec["height"] == 120 and rec["frame_index"] == f
