@@ -35,20 +35,44 @@ constexpr int kPx = 4;              // pixels per tile
 constexpr int kN = 32;              // MMA N = 8 step slots x 4 pixels (slot 7 unused)
 constexpr int kR = 12;              // tiles per K-block -> 48 pixels per CTA
 constexpr int kPT = kPx * kR;
-constexpr int kBufs = 5;            // TMEM accumulator buffers: HH | M | LL, 32 columns each
-constexpr int kBufCols = 3 * kN;
-constexpr int kACol = kBufs * kBufCols;   // 480: two weight slots of 16 columns (hi plane 8 | lo plane 8)
+#ifndef Y2_TC2_PLANES
+#define Y2_TC2_PLANES 3
+#endif
+// Y2_TC2_PLANES = 2: the LL product leaves the tensor core (LL = dp4a(w_lo, x_lo) + half on the CUDA cores, one more FMA-pipe instruction per
+// step), a tile is HH | M = 64 columns and SEVEN tiles are in flight in tensor memory instead of five (the kernel is bound by
+// steps in flight / hand-off round trip), three MMAs and six loads per tile instead of four and nine.
+constexpr int kPlanes = Y2_TC2_PLANES;
+constexpr bool kLLCuda = kPlanes == 2;
+constexpr int kBufs = kLLCuda ? 7 : 5;   // TMEM accumulator buffers: HH | M [| LL], 32 columns each
+constexpr int kBufCols = kPlanes * kN;
+constexpr int kACol = kBufs * kBufCols;   // 480 / 448: two weight slots of 16 columns (hi plane 8 | lo plane 8)
+constexpr int kXlBytes = kLLCuda ? 2 * 12 * 128 : 0;   // compact copy of the lo activation bytes for the CUDA-core LL: [K-block parity][tile][step][pixel] words
 constexpr int kBRing = 12;          // activation tile ring (hi 1 KB | lo 1 KB) = the kR tiles of one K-block (see the go[] comment in the kernel)
 constexpr int kWRing = 3;           // weight K-block ring in shared memory
-constexpr int kEpiWarps = 12;       // warps 0-11 (three warpgroups): group kg = warp/4, TMEM lane quadrant = warp%4
-constexpr int kBuilders = 3;        // warps 12-14: builder bw takes the tile PAIRS (2j, 2j+1) with j = bw (mod 3); warp 15 idles
-constexpr int kIssuer = 16;         // warps 16-19: issuer iw takes the tiles r = iw (mod 4).  One warp issues one MMA per ~29 cycles
+#ifndef Y2_TC2_GROUPS
+#define Y2_TC2_GROUPS 4
+#endif
+constexpr int kGroups = Y2_TC2_GROUPS;   // epilogue warpgroups.  A group's tile costs wait (~250 cycles) + read-out (~250) + compute (~340) per warp
+                                    //   (role profile, profiles/r1_tc2_role_profile.txt): with three warps per SM sub-partition the ALU pipe idles
+                                    //   ~45 % of the time, so FOUR groups share it.  Registers: 4 groups cannot hold 96 + 16 each, so a tile is read
+                                    //   as its 28 live columns (84 registers) and the chain state U lives in shared memory between tiles.
+constexpr int kTPG = kR / kGroups;  // tiles per group per K-block
+constexpr int kEpiWarps = 4 * kGroups;   // warps 0..: group kg = warp/4, TMEM lane quadrant = warp%4
+constexpr int kBuilders = 3;        // next warpgroup: builder bw takes the tile PAIRS (2j, 2j+1) with j = bw (mod 3); its fourth warp idles
+constexpr int kIssuer = kEpiWarps + 4;   // last warpgroup: issuer iw takes the tiles r = iw (mod 4).  One warp issues one MMA per ~29 cycles
 constexpr int kIssuers = 4;         //   (profiles/microbench/umma_issue.cu) and pays ~100 cycles per mbarrier wait: four warps keep the
                                     //   per-tile issue cost (wait + 4 MMAs + commit, ~300 cycles) below the epilogue's ~140 cycles per tile
-constexpr int kThreads = 20 * 32;   // five warpgroups: 65536 / 640 = 102 registers per thread at launch (96 allocated), then
-constexpr int kEpiRegs = 128;       //   setmaxnreg moves 8 x 32 x (96-48) = 12288 registers from the helper warps to the 12 epilogue warps (128 each:
-constexpr int kHelperRegs = 48;     //   a whole tile = 96 registers is loaded at once).  The CTA pool only holds what the helpers release.
-static_assert(kBRing == kR && kR % kIssuers == 0 && kR % 3 == 0 && (kR / 2) % kBuilders == 0, "ring = one K-block; see go[]");
+constexpr int kThreads = (kEpiWarps + 8) * 32;   // 3 groups: 640 threads, 96 registers at launch; 4 groups: 768 threads, 80 at launch.  Then
+constexpr int kEpiRegs = kGroups == 3 ? 128 : 96;   // setmaxnreg moves 8 x 32 x (launch - 48) registers from the helper warps to the epilogue warps
+constexpr int kHelperRegs = 48;     //   (+32 each for 3 groups, +16 for 4).  The CTA pool only holds what the helpers release.
+#ifndef Y2_TC2_RD_HANDSHAKE
+#define Y2_TC2_RD_HANDSHAKE 1
+#endif
+constexpr bool kRdHandshake = kLLCuda || Y2_TC2_RD_HANDSHAKE != 0;   // builders also wait for the READ-OUT of a slot's previous tile (see the builder loop)
+constexpr bool kUShared = kGroups != 3;
+static_assert(!kLLCuda || kUShared, "the two-plane build uses the four-group epilogue");
+constexpr int kUBytes = kUShared ? kEpiWarps * 32 * kTPG * 16 : 0;   // chain state [tile of the group][epilogue thread] x 4 pixels
+static_assert(kBRing == kR && kR % kIssuers == 0 && kR % kGroups == 0 && (kR / 2) % kBuilders == 0, "ring = one K-block; see go[]");
 constexpr int kWBytes = kM * 64;    // one K-block of weights: [row][hi 32 B | lo 32 B], 16-byte chunks XOR-swizzled by (row>>1)&3
 constexpr int kBBytes = kN * 32;    // one plane of one activation tile
 
@@ -59,7 +83,7 @@ __device__ __forceinline__ void mbar_init(void *bar, unsigned count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 #ifdef Y2_TC2_PROFILE
-__device__ int g_tc2_dbg[20 * 4];
+__device__ int g_tc2_dbg[32 * 4];
 __device__ int g_tc2_abort;
 // debug build: a wait that does not complete within ~0.1 s records (line, barrier offset, parity) for its warp and gives up,
 // so that a protocol deadlock ends the kernel and can be read back instead of hanging the GPU
@@ -70,8 +94,10 @@ __device__ __forceinline__ void mbar_wait_dbg(void *bar, unsigned parity, int li
         unsigned ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (ok) return;
-        if (clock64() - t0 > 200000000LL || *(volatile int *)&g_tc2_abort) {
-            if (blockIdx.x == 1 && blockIdx.y == 0 && g_tc2_dbg[(threadIdx.x >> 5) * 4] == 0) {
+        const long long waited = clock64() - t0;
+        if (waited > 200000000LL || *(volatile int *)&g_tc2_abort) {
+            // record only waits that were really stuck (not the unsatisfied waits a released warp runs into after the abort)
+            if (waited > 20000000LL && blockIdx.x == 1 && blockIdx.y == 0 && g_tc2_dbg[(threadIdx.x >> 5) * 4] == 0) {
                 int *d = g_tc2_dbg + (threadIdx.x >> 5) * 4;
                 d[0] = line; d[1] = (int)(smem_u32(bar)); d[2] = (int)parity;
             }
@@ -142,6 +168,16 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, int *r)
                    "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, int *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4(unsigned taddr, int *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_st8(unsigned taddr, const uint4 &a, const uint4 &b)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(a.x), "r"(a.y), "r"(a.z),
@@ -154,6 +190,11 @@ __device__ __forceinline__ void reg_fence16(int *r)
     asm volatile(""
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
                    "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
+}
+__device__ __forceinline__ void reg_fence12(int *r)
+{
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11])::"memory");
 }
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
 {
@@ -178,7 +219,7 @@ __host__ __device__ constexpr unsigned idesc_i8(int a_signed, int b_signed)
 __host__ __device__ inline int operand_off(int row, int k) { return (((row >> 3) * 2 + (k >> 4)) * 8 + (row & 7)) * 16 + (k & 15); }
 
 #ifdef Y2_TC2_PROFILE
-__device__ long long g_tc2_prof[20 * 8];
+__device__ long long g_tc2_prof[32 * 8];
 #define PROF_DECL long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_ = clock64(); const long long pstart_ = pt_;
 #define PROF_ADD(i) do { long long n_ = clock64(); prof_[i] += n_ - pt_; pt_ = n_; } while (0)
 #define PROF_END do { prof_[7] = clock64() - pstart_; if (blockIdx.x == 1 && blockIdx.y == 0 && lane == 0) for (int i_ = 0; i_ < 8; ++i_) g_tc2_prof[warp * 8 + i_] = prof_[i_]; } while (0)
@@ -218,6 +259,13 @@ __device__ __forceinline__ int tc2_step(int acc, int hh, int mm, int ll)
     return __viaddmin_s32_relu(acc, d, 65535);             // VIADDMNMX.RELU: max(min(acc + d, 65535), 0)
 }
 
+__device__ __forceinline__ int dp4a_uu(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return (int)d;
+}
+
 template <int KS, int SO>
 __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Params p)
 {
@@ -226,15 +274,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sW = smem;                                    // kWRing x 8 KB
     unsigned char *sB = sW + kWRing * kWBytes;                   // kBRing x (hi 1 KB | lo 1 KB); a builder pair = two consecutive slots
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sB + kBRing * 2 * kBBytes);
+    int4 *sU = reinterpret_cast<int4 *>(sB + kBRing * 2 * kBBytes);   // chain state between tiles (four-group build)
+    uint4 *sXl = reinterpret_cast<uint4 *>(sB + kBRing * 2 * kBBytes + kUBytes);   // two-plane build: [b & 1][tile r][step] x 4 pixels
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sB + kBRing * 2 * kBBytes + kUBytes + kXlBytes);
     unsigned long long *w_full = bars, *w_empty = w_full + kWRing, *a_full = w_empty + kWRing, *a_empty = a_full + 2,
-                       *go = a_empty + 2, *mma_done = go + kBRing;
+                       *go = a_empty + 2, *mma_done = go + kBRing, *rd_done = mma_done + kBRing;   // rd_done[kBRing]: tile read out by all four warps of its group (two-plane build)
     // go[r]: tile r of the current K-block may be issued = its activation tile is built (1 arrival, builder) AND its TMEM buffer
     // it % 5 has been read out by the epilogue of tile it-5 (4 arrivals, one per warp; pre-arrived for the first five tiles).
     // The ring has kR = 12 slots = one K-block, a multiple of the number of issuers (4), epilogue groups (3) and builders: every
     // barrier's consecutive phases are then awaited by the SAME warp in program order, which the parity wait needs (a warp that
     // could start waiting two phases ahead would see the previous phase's parity and fall through).
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(mma_done + kBRing + 1);
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(rd_done + kBRing + 1);
     int *pxtab = reinterpret_cast<int *>(tmem_slot + 4);         // [48][4]: smem pixel offset for tap rows 0..2, valid flag
     int *rowinfo = pxtab + kPT * 4;                              // [32][2]: per staged row slot: first needed column, prefix of the copy table
     int2 *ctab = reinterpret_cast<int2 *>(rowinfo + 64);         // copy table of one C4 group plane: (global pixel offset, smem pixel offset)
@@ -250,7 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
     const long long row_first = pix0 / p.W;                      // global row (frame*H + y) of the first pixel
 
     if (tid == 0) {
-        for (int i = 0; i < kWRing; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 4); }
+        for (int i = 0; i < kWRing; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], kLLCuda ? 4 + kEpiWarps : 4); }
+        for (int i = 0; i < kBRing; ++i) mbar_init(&rd_done[i], 4);
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], kIssuers); }
         for (int i = 0; i < kBRing; ++i) { mbar_init(&go[i], 5); mbar_init(&mma_done[i], 1); }
         for (int i = 0; i < kBufs; ++i)
@@ -374,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                         umma_i8_ts(d0, ah, dBh, idesc_i8(1, 1), 0);            // HH
                         umma_i8_ts(d0 + kN, ah, dBl, idesc_i8(1, 0), 0);       // M  = hi*lo
                         umma_i8_ts(d0 + kN, al, dBh, idesc_i8(0, 1), 1);       //    + lo*hi
-                        umma_i8_ts(d0 + 2 * kN, al, dBl, idesc_i8(0, 0), 0);   // LL
+                        if constexpr (!kLLCuda) umma_i8_ts(d0 + 2 * kN, al, dBl, idesc_i8(0, 0), 0);   // LL
                         umma_commit(&mma_done[r]);                             // epilogue (tile ready) and builders (slot free) wait on it
                         if (j == kR / kIssuers - 1) umma_commit(&a_empty[b & 1]);   // this warp's reads of the weight slot are done
                     }
@@ -439,6 +490,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                         mbar_wait(&mma_done[2 * j], (b - 1) & 1);
                         mbar_wait(&mma_done[2 * j + 1], (b - 1) & 1);
                     }
+                    if constexpr (kRdHandshake) {
+                        // every warp of the tiles' epilogue groups has READ OUT the previous K-block's tiles of these slots.  This (a) keeps
+                        // mma_done[r] from completing a second phase before a late warp has tested the first (seven tiles in flight leave
+                        // one hop of slack otherwise - measured as hangs), and (b) protects the compact lo bytes: a group reads out tile
+                        // (b-1, r) only after it has finished computing tile (b-2, r), whose copy this build overwrites
+                        if (b >= 1) {
+                            mbar_wait(&rd_done[2 * j], (b - 1) & 1);
+                            mbar_wait(&rd_done[2 * j + 1], (b - 1) & 1);
+                        }
+                    }
                     PROF_ADD(1);
                     unsigned char *bh = sB + (j * 4) * kBBytes;
                     if (has) {
@@ -455,6 +516,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                         *reinterpret_cast<unsigned *>(bh + kBBytes + off0) = lo0;
                         *reinterpret_cast<unsigned *>(bh + 2 * kBBytes + off0) = hi1;
                         *reinterpret_cast<unsigned *>(bh + 3 * kBBytes + off0) = lo1;
+                        if constexpr (kLLCuda) {            // entry e = step*4 + pixel of tiles 2j, 2j+1
+                            unsigned *xl = reinterpret_cast<unsigned *>(sXl) + ((b & 1) * kBRing + 2 * j) * 32 + lane;
+                            xl[0] = lo0;
+                            xl[32] = lo1;
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -465,13 +531,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             PROF_END;
         }
     } else {
-        // ===== epilogue warps: thread = one output channel (TMEM lane); warp group kg = warp/4 takes the tiles r = kg (mod 3) =====
+        // ===== epilogue warps: thread = one output channel (TMEM lane); warp group kg = warp/4 takes the tiles r = kg (mod kGroups) =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
         const int q4 = warp & 3, kg = warp >> 2;
         const int row = q4 * 32 + lane;
         const int m = mtile * kM + row;
         const unsigned lane_base = tmem + ((unsigned)(q4 * 32) << 16);
-        int U[kR / 3][kPx];
+        int U[kUShared ? 1 : kTPG][kPx];
+        int4 *myU = sU + tid;                       // [tile of the group] at stride kEpiWarps * 32
         {
             long long bv = (m < p.OFM) ? (long long)p.bias[m] : 0;
             long long base = round_shift64(bv, p.sb);
@@ -479,10 +546,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             long long boff = base + 32768;
             if (boff > 65535 + rb) boff = 65535 + rb;
             if (boff < -rb) boff = -rb;
+            if constexpr (kUShared) {
 #pragma unroll
-            for (int r = 0; r < kR / 3; ++r)
+                for (int r = 0; r < kTPG; ++r) myU[r * kEpiWarps * 32] = make_int4((int)boff, (int)boff, (int)boff, (int)boff);
+            } else {
 #pragma unroll
-                for (int j = 0; j < kPx; ++j) U[r][j] = (int)boff;
+                for (int r = 0; r < kTPG; ++r)
+#pragma unroll
+                    for (int j = 0; j < kPx; ++j) U[r][j] = (int)boff;
+            }
         }
         // copy one K-block of weights shared memory -> registers -> tensor memory (A operand slot bn & 1)
         auto stage_weights = [&](int bn) {
@@ -502,52 +574,112 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
         };
         PROF_DECL
         if (kg == 0) stage_weights(0);
-        int tb = kg;                                // TMEM buffer it % 5 of this group's next tile (stride 3)
+        int tb = kg % kBufs;                        // TMEM buffer it % 5 of this group's next tile (stride kGroups)
         for (int b = 0; b < p.nkb; ++b) {
             PROF_ADD(4);
-            if (b + 1 < p.nkb && (b + 1) % 3 == kg) stage_weights(b + 1);
+            if (b + 1 < p.nkb && (b + 1) % kGroups == kg) stage_weights(b + 1);
+            unsigned wl[8];                         // two-plane build: the lo bytes of this channel's weights for the 7 steps of the K-block
+            if constexpr (kLLCuda) {
+                const int s = b % kWRing;
+                mbar_wait(&w_full[s], (b / kWRing) & 1);
+                const uint4 *src = reinterpret_cast<const uint4 *>(sW + s * kWBytes + row * 64);
+                const int sw = (row >> 1) & 3;
+                const uint4 c2 = src[2 ^ sw], c3 = src[3 ^ sw];
+                wl[0] = c2.x; wl[1] = c2.y; wl[2] = c2.z; wl[3] = c2.w; wl[4] = c3.x; wl[5] = c3.y; wl[6] = c3.z; wl[7] = 0u;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&w_empty[s]);
+            }
             PROF_ADD(0);
 #pragma unroll
-            for (int rr = 0; rr < kR / 3; ++rr) {
-                const int r = 3 * rr + kg;
+            for (int rr = 0; rr < kTPG; ++rr) {
+                const int r = kGroups * rr + kg;
                 PROF_ADD(4);
                 mbar_wait(&mma_done[r], b & 1);
                 PROF_ADD(1);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const unsigned base = lane_base + tb * kBufCols;
                 int hh[32], mm[32], ll[32];      // column n = step*4 + pixel
-                tmem_ld16(base, hh); tmem_ld16(base + 16, hh + 16);
-                tmem_ld16(base + kN, mm); tmem_ld16(base + kN + 16, mm + 16);
-                tmem_ld16(base + 2 * kN, ll); tmem_ld16(base + 2 * kN + 16, ll + 16);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                reg_fence16(hh); reg_fence16(hh + 16); reg_fence16(mm); reg_fence16(mm + 16); reg_fence16(ll); reg_fence16(ll + 16);
+                if constexpr (kLLCuda) {         // HH and M only: 56 registers
+                    tmem_ld16(base, hh); tmem_ld8(base + 16, hh + 16); tmem_ld4(base + 24, hh + 24);
+                    tmem_ld16(base + kN, mm); tmem_ld8(base + kN + 16, mm + 16); tmem_ld4(base + kN + 24, mm + 24);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    reg_fence16(hh); reg_fence12(hh + 16); reg_fence16(mm); reg_fence12(mm + 16);
+                } else if constexpr (kUShared) {        // only the 28 live columns: 84 registers
+                    tmem_ld16(base, hh); tmem_ld8(base + 16, hh + 16); tmem_ld4(base + 24, hh + 24);
+                    tmem_ld16(base + kN, mm); tmem_ld8(base + kN + 16, mm + 16); tmem_ld4(base + kN + 24, mm + 24);
+                    tmem_ld16(base + 2 * kN, ll); tmem_ld8(base + 2 * kN + 16, ll + 16); tmem_ld4(base + 2 * kN + 24, ll + 24);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    reg_fence16(hh); reg_fence12(hh + 16); reg_fence16(mm); reg_fence12(mm + 16); reg_fence16(ll); reg_fence12(ll + 16);
+                } else {
+                    tmem_ld16(base, hh); tmem_ld16(base + 16, hh + 16);
+                    tmem_ld16(base + kN, mm); tmem_ld16(base + kN + 16, mm + 16);
+                    tmem_ld16(base + 2 * kN, ll); tmem_ld16(base + 2 * kN + 16, ll + 16);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    reg_fence16(hh); reg_fence16(hh + 16); reg_fence16(mm); reg_fence16(mm + 16); reg_fence16(ll); reg_fence16(ll + 16);
+                }
                 // everything is in registers: tile it+5 (ring slot r+5 mod 12) may overwrite this TMEM buffer
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&go[r + kBufs < kR ? r + kBufs : r + kBufs - kR]);
+                if (lane == 0) {
+                    mbar_arrive(&go[r + kBufs < kR ? r + kBufs : r + kBufs - kR]);
+                    if constexpr (kRdHandshake) mbar_arrive(&rd_done[r]);
+                }
                 PROF_ADD(2);
+                if constexpr (kLLCuda) {
+                    constexpr unsigned kHalfLL = SO <= 15 ? 1u << (SO - 1) : 0u;   // so >= 16: the constant enters through M (K row 28)
+                    const int4 u = myU[rr * kEpiWarps * 32];
+                    U[0][0] = u.x; U[0][1] = u.y; U[0][2] = u.z; U[0][3] = u.w;
+                    const uint4 *xlp = sXl + ((b & 1) * kBRing + r) * 8;
 #pragma unroll
-                for (int n = 0; n < kSteps * kPx; ++n) U[rr][n % kPx] = tc2_step<SO>(U[rr][n % kPx], hh[n], mm[n], ll[n]);
-                tb = tb >= 2 ? tb - 2 : tb + 3;
+                    for (int sidx = 0; sidx < kSteps; ++sidx) {
+                        const uint4 xv = xlp[sidx];     // same address in every lane: one broadcast read
+                        const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                        for (int px = 0; px < kPx; ++px) {
+                            const int n = sidx * kPx + px;
+                            U[0][px] = tc2_step<SO>(U[0][px], hh[n], mm[n], dp4a_uu(wl[sidx], xs[px], kHalfLL));
+                        }
+                    }
+                    myU[rr * kEpiWarps * 32] = make_int4(U[0][0], U[0][1], U[0][2], U[0][3]);
+                } else if constexpr (kUShared) {
+                    const int4 u = myU[rr * kEpiWarps * 32];
+                    U[0][0] = u.x; U[0][1] = u.y; U[0][2] = u.z; U[0][3] = u.w;
+#pragma unroll
+                    for (int n = 0; n < kSteps * kPx; ++n) U[0][n % kPx] = tc2_step<SO>(U[0][n % kPx], hh[n], mm[n], ll[n]);
+                    myU[rr * kEpiWarps * 32] = make_int4(U[0][0], U[0][1], U[0][2], U[0][3]);
+                } else {
+#pragma unroll
+                    for (int n = 0; n < kSteps * kPx; ++n) U[rr][n % kPx] = tc2_step<SO>(U[rr][n % kPx], hh[n], mm[n], ll[n]);
+                }
+                tb = tb >= kBufs - kGroups ? tb - (kBufs - kGroups) : tb + kGroups;
                 PROF_ADD(3);
             }
         }
         PROF_END;
         if (m < p.OFM) {
 #pragma unroll
-            for (int rr = 0; rr < kR / 3; ++rr)
+            for (int rr = 0; rr < kTPG; ++rr) {
+                int Uo[kPx];
+                if constexpr (kUShared) {
+                    const int4 u = myU[rr * kEpiWarps * 32];
+                    Uo[0] = u.x; Uo[1] = u.y; Uo[2] = u.z; Uo[3] = u.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kPx; ++j) Uo[j] = U[kUShared ? 0 : rr][j];
+                }
 #pragma unroll
                 for (int j = 0; j < kPx; ++j) {
-                    const long long gp = pix0 + (3 * rr + kg) * kPx + j;
+                    const long long gp = pix0 + (kGroups * rr + kg) * kPx + j;
                     if (gp >= npix) continue;
                     const long long grow = gp / p.W;
                     const int x = (int)(gp - grow * p.W);
                     const long long f = grow / p.H;
                     const int y = (int)(grow - f * p.H);
-                    int a = U[rr][j] - 32768;
+                    int a = Uo[j] - 32768;
                     if (p.leaky && a < 0) a = a / 10;
                     p.out[f * p.out_frame_stride + (((long long)(m >> 2) * p.H + y) * p.W + x) * 4 + (m & 3)] = (int16_t)a;
                 }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -646,7 +778,7 @@ int launch_conv_i16_tc2(const ConvFastParams &cp, int ksize, cudaStream_t st, co
     p.rows_max = (kPT - 1) / cp.W + 2 + (ksize - 1) + 1;
     if (p.rows_max > 30) return -1;                     // rowinfo[] holds 32 staged rows
     p.ctab_cap = (p.rows_max - 1) * cp.W;
-    const size_t fixed = (size_t)kWRing * kWBytes + (size_t)kBRing * 2 * kBBytes + 512 + kPT * 16 + 256 + (size_t)p.ctab_cap * 8;
+    const size_t fixed = (size_t)kWRing * kWBytes + (size_t)kBRing * 2 * kBBytes + kUBytes + kXlBytes + 768 + kPT * 16 + 256 + (size_t)p.ctab_cap * 8;
     const size_t per_group = (size_t)p.rows_max * p.PW * 8;
     int gs = (int)((200 * 1024 - fixed) / (2 * per_group));
     if (gs < 1) return -1;
@@ -662,16 +794,16 @@ int launch_conv_i16_tc2(const ConvFastParams &cp, int ksize, cudaStream_t st, co
 #ifdef Y2_TC2_PROFILE
     {
         cudaStreamSynchronize(st);
-        long long h[20 * 8];
+        long long h[32 * 8];
         cudaMemcpyFromSymbol(h, g_tc2_prof, sizeof(h));
         fprintf(stderr, "tc2 profile (CTA 1,0) G=%d W=%d nkb=%d: per warp [w_stage|wait a, wait b_full|mma_done, wait t_empty|ld, issue|compute, other, -, -, total]\n", cp.G, cp.W, p.nkb);
-        int hd[20 * 4], ab = 0;
+        int hd[32 * 4], ab = 0;
         cudaMemcpyFromSymbol(hd, g_tc2_dbg, sizeof(hd));
         cudaMemcpyFromSymbol(&ab, g_tc2_abort, sizeof(ab));
         if (ab) {
             fprintf(stderr, "tc2 DEADLOCK (CTA 1,0): per warp [line, barrier smem addr, parity]\n");
             for (int w = 0; w < kThreads / 32; ++w) fprintf(stderr, "  warp %2d: line %d bar 0x%x parity %d\n", w, hd[w * 4], hd[w * 4 + 1], hd[w * 4 + 2]);
-            int z[20 * 4] = {0}; ab = 0;
+            int z[32 * 4] = {0}; ab = 0;
             cudaMemcpyToSymbol(g_tc2_dbg, z, sizeof(z)); cudaMemcpyToSymbol(g_tc2_abort, &ab, sizeof(ab));
         }
         for (int w = 0; w < kThreads / 32; ++w) {
