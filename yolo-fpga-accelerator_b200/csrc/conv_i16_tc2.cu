@@ -69,6 +69,15 @@ constexpr int kHelperRegs = 48;     //   (+32 each for 3 groups, +16 for 4).  Th
 #define Y2_TC2_RD_HANDSHAKE 1
 #endif
 constexpr bool kRdHandshake = kLLCuda || Y2_TC2_RD_HANDSHAKE != 0;   // builders also wait for the READ-OUT of a slot's previous tile (see the builder loop)
+#ifndef Y2_TC2_SLEEP_BUILDER
+#define Y2_TC2_SLEEP_BUILDER 0
+#endif
+#ifndef Y2_TC2_SLEEP_ISSUER
+#define Y2_TC2_SLEEP_ISSUER 0
+#endif
+#ifndef Y2_TC2_SLEEP_EPI
+#define Y2_TC2_SLEEP_EPI 0
+#endif
 constexpr bool kUShared = kGroups != 3;
 static_assert(!kLLCuda || kUShared, "the two-plane build uses the four-group epilogue");
 constexpr int kUBytes = kUShared ? kEpiWarps * 32 * kTPG * 16 : 0;   // chain state [tile of the group][epilogue thread] x 4 pixels
@@ -133,9 +142,37 @@ __device__ __forceinline__ unsigned mbar_test(void *bar, unsigned parity)   // n
         : "memory");
     return ok;
 }
+// wait with a back-off between probes: a failed try_wait returns after ~60 cycles, and the probe loops of the ~9 warps that are waiting at
+// any time were 20 % of all issued instructions (ncu source counters) on sub-partitions whose issue slots are 80 % busy
+template <int NS>
+__device__ __forceinline__ void mbar_wait_sleep(void *bar, unsigned parity)
+{
+    if constexpr (NS == 0) {
+        mbar_wait(bar, parity);
+    } else {
+#ifdef Y2_TC2_PROFILE
+        mbar_wait(bar, parity);
+#else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "WAIT_LOOP:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra DONE;\n\t"
+            "nanosleep.u32 %2;\n\t"
+            "bra WAIT_LOOP;\n\t"
+            "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "n"(NS)
+            : "memory");
+#endif
+    }
+}
 __device__ __forceinline__ void mbar_arrive(void *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive from the lanes where `on` is set, as a predicated instruction (no branch, no convergence barrier around it)
+__device__ __forceinline__ void mbar_arrive_if(void *bar, bool on)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar)), "r"((int)on) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
 {
@@ -177,6 +214,21 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, int *r)
 __device__ __forceinline__ void tmem_ld4(unsigned taddr, int *r)
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+// the 28 live columns of one plane (x16 + x8 + x4) from ONE address operand: one R2UR per plane instead of one per load
+__device__ __forceinline__ void tmem_ld28(unsigned taddr, int *r)
+{
+    asm volatile(
+        "{\n\t.reg .b32 a1, a2;\n\t"
+        "add.u32 a1, %28, 16;\n\t"
+        "add.u32 a2, %28, 24;\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%28];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [a1];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%24,%25,%26,%27}, [a2];\n\t}"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27])
+        : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_st8(unsigned taddr, const uint4 &a, const uint4 &b)
 {
@@ -290,7 +342,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
     int2 *ctab = reinterpret_cast<int2 *>(rowinfo + 64);         // copy table of one C4 group plane: (global pixel offset, smem pixel offset)
     uint2 *sX = reinterpret_cast<uint2 *>(ctab + p.ctab_cap);    // 2 chunks x GS groups x rows_max x PW pixels
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the warp index through a shuffle: the compiler then knows it (and every TMEM address / role branch derived from it) is warp-uniform
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const long long npix = (long long)p.B * p.H * p.W;
     const long long pix0 = (long long)blockIdx.x * kPT;
     const int mtile = blockIdx.y;
@@ -379,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
-    const unsigned tmem = *tmem_slot;
+    const unsigned tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler: TMEM addresses live in uniform registers
 
     if (warp >= kEpiWarps) {
         // the two helper warpgroups hand most of their registers to the three epilogue warpgroups
@@ -416,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
 #pragma unroll
                 for (int j = 0; j < kR / kIssuers; ++j) {
                     const int r = iw + j * kIssuers;
-                    mbar_wait(&go[r], b & 1);
+                    mbar_wait_sleep<Y2_TC2_SLEEP_ISSUER>(&go[r], b & 1);
                     PROF_ADD(1);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     if (elected) {
@@ -486,8 +539,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                 for (int jj = 0; jj < kR / 2 / kBuilders; ++jj) {
                     const int j = bw + jj * kBuilders;      // pair index in the K-block: ring slots 2j, 2j+1
                     PROF_ADD(4);
-                    if (b >= 1) {                           // the MMAs of the previous K-block's tiles in both slots have read them
-                        mbar_wait(&mma_done[2 * j], (b - 1) & 1);
+                    if (b >= 1 && !kRdHandshake) {          // the MMAs of the previous K-block's tiles in both slots have read them
+                        mbar_wait(&mma_done[2 * j], (b - 1) & 1);    // (implied by rd_done below when the handshake is on: a tile is read out after its MMAs)
                         mbar_wait(&mma_done[2 * j + 1], (b - 1) & 1);
                     }
                     if constexpr (kRdHandshake) {
@@ -496,8 +549,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                         // one hop of slack otherwise - measured as hangs), and (b) protects the compact lo bytes: a group reads out tile
                         // (b-1, r) only after it has finished computing tile (b-2, r), whose copy this build overwrites
                         if (b >= 1) {
-                            mbar_wait(&rd_done[2 * j], (b - 1) & 1);
-                            mbar_wait(&rd_done[2 * j + 1], (b - 1) & 1);
+                            mbar_wait_sleep<Y2_TC2_SLEEP_BUILDER>(&rd_done[2 * j], (b - 1) & 1);
+                            mbar_wait_sleep<Y2_TC2_SLEEP_BUILDER>(&rd_done[2 * j + 1], (b - 1) & 1);
                         }
                     }
                     PROF_ADD(1);
@@ -524,7 +577,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(&go[2 * j]); mbar_arrive(&go[2 * j + 1]); }
+                    mbar_arrive_if(&go[2 * j], lane == 0);
+                    mbar_arrive_if(&go[2 * j + 1], lane == 0);
                     PROF_ADD(2);
                 }
             }
@@ -594,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             for (int rr = 0; rr < kTPG; ++rr) {
                 const int r = kGroups * rr + kg;
                 PROF_ADD(4);
-                mbar_wait(&mma_done[r], b & 1);
+                mbar_wait_sleep<Y2_TC2_SLEEP_EPI>(&mma_done[r], b & 1);
                 PROF_ADD(1);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const unsigned base = lane_base + tb * kBufCols;
@@ -605,9 +659,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     reg_fence16(hh); reg_fence12(hh + 16); reg_fence16(mm); reg_fence12(mm + 16);
                 } else if constexpr (kUShared) {        // only the 28 live columns: 84 registers
-                    tmem_ld16(base, hh); tmem_ld8(base + 16, hh + 16); tmem_ld4(base + 24, hh + 24);
-                    tmem_ld16(base + kN, mm); tmem_ld8(base + kN + 16, mm + 16); tmem_ld4(base + kN + 24, mm + 24);
-                    tmem_ld16(base + 2 * kN, ll); tmem_ld8(base + 2 * kN + 16, ll + 16); tmem_ld4(base + 2 * kN + 24, ll + 24);
+                    tmem_ld28(base, hh);
+                    tmem_ld28(base + kN, mm);
+                    tmem_ld28(base + 2 * kN, ll);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     reg_fence16(hh); reg_fence12(hh + 16); reg_fence16(mm); reg_fence12(mm + 16); reg_fence16(ll); reg_fence12(ll + 16);
                 } else {
@@ -620,10 +674,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                 // everything is in registers: tile it+5 (ring slot r+5 mod 12) may overwrite this TMEM buffer
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&go[r + kBufs < kR ? r + kBufs : r + kBufs - kR]);
-                    if constexpr (kRdHandshake) mbar_arrive(&rd_done[r]);
-                }
+                mbar_arrive_if(&go[r + kBufs < kR ? r + kBufs : r + kBufs - kR], lane == 0);
+                if constexpr (kRdHandshake) mbar_arrive_if(&rd_done[r], lane == 0);
                 PROF_ADD(2);
                 if constexpr (kLLCuda) {
                     constexpr unsigned kHalfLL = SO <= 15 ? 1u << (SO - 1) : 0u;   // so >= 16: the constant enters through M (K row 28)
