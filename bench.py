@@ -236,12 +236,12 @@ def main():
     chunks = (B + y.max_batch - 1) // y.max_batch       # layer_times covers the LAST chunk of the step
     last_chunk = B - (chunks - 1) * y.max_batch
     # dominant kernel = conv_i16_tc2_kernel<3,so> (tcgen05): the 3x3 layers the network executor puts on the tensor cores
-    # (csrc/capi.cu auto policy: full 128-channel tiles, >= 128 input channels, <= 26 wide); 62 % of the device time in the
+    # (csrc/capi.cu auto policy: full 128-channel tiles, >= 128 input channels, <= 52 wide); ~70 % of the device time in the
     # ncu launch list of this command (profiles/r1_bench_launches_ncu.csv)
     def on_tc2(l):
-        return l.type == ycfg.CONV and l.size == 3 and l.n % 128 == 0 and l.c >= 128 and l.w <= 26 and os.environ.get("YOLO2CUDA_TC", "") == ""
+        return l.type == ycfg.CONV and l.size == 3 and l.n % 128 == 0 and l.c >= 128 and l.w <= 52 and os.environ.get("YOLO2CUDA_TC", "") == ""
     dom = [(i, l) for i, l in enumerate(net.layers) if on_tc2(l)]
-    dom_name = "conv_i16_tc2_kernel<3,14> (tcgen05.mma kind::i8 + exact CUDA-core round-and-saturate; 3x3 layers <= 26 wide)"
+    dom_name = "conv_i16_tc2_kernel<3,14> (tcgen05.mma kind::i8 + exact CUDA-core round-and-saturate; 3x3 layers <= 52 wide)"
     if not dom:   # YOLO2CUDA_TC forced: fall back to "all 3x3 conv layers"
         dom = [(i, l) for i, l in enumerate(net.layers) if l.type == ycfg.CONV and l.size == 3]
         dom_name = "all 3x3 conv layers (YOLO2CUDA_TC=%s)" % os.environ.get("YOLO2CUDA_TC")

@@ -823,10 +823,12 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                     l.cp = p;
                     // tensor-core path: wide layers only (a CTA covers 128 output channels)
                     l.tc = ctx->use_tc > 0 && e == 2 && so >= 8 && so <= 22 && l.d.n >= ctx->tc_min_ofm;
-                    // auto: the tcgen05 kernel where it measured faster than the CUDA-core kernel (profiles/r1_layer_table_int16_b256_tc2.json):
-                    // full 128-channel tiles on the narrow (<= 26 wide) deep layers; both paths are bit-exact, so mixing them is safe
-                    if (ctx->use_tc < 0 && e == 2 && so >= 8 && so <= 22 && l.d.n % 128 == 0 && l.d.c >= 128 &&
-                        ((l.d.size == 3 && l.d.w <= 26) || (l.d.size == 1 && l.d.w <= 13)))
+                    // auto: the tcgen05 kernel where it measured faster than the CUDA-core kernel (profiles/r1_layer_table_int16_b128_tc2_final.json
+                    // against r1_layer_table_int16_b256.json): 3x3 layers up to 52 wide with full 128-channel tiles, deep 1x1 layers up to
+                    // 26 wide; both paths are bit-exact, so mixing them is safe
+                    if (ctx->use_tc < 0 && e == 2 && so >= 8 && so <= 22 &&
+                        ((l.d.size == 3 && l.d.w <= 52 && l.d.n % 128 == 0 && l.d.c >= 128) ||
+                         (l.d.size == 1 && l.d.w <= 26 && l.d.n >= 256 && l.d.c >= 512)))
                         l.tc = true;
                     if (l.tc) {
                         const bool v2 = ctx->use_tc != 1;

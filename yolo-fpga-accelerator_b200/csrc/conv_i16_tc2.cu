@@ -296,11 +296,22 @@ struct Tc2Params {
 
 // one exact step of the chain from the three int8-plane partial sums.  Everything but the last instruction is independent
 // of the accumulator, so the serial chain through a tile is one VIADDMNMX per step and the rest is free to overlap.
+#ifndef Y2_TC2_HH_COPIES
+#define Y2_TC2_HH_COPIES 0
+#endif
+// With Y2_TC2_HH_COPIES the HH product is issued 2^(16-so) times into the same accumulator (so = 14, 15: 4 or 2 MMAs), so the tensor core
+// delivers HH * 2^(16-so) and the step is THREE instructions (IMAD, LEA.HI.SX32, VIADDMNMX) - the kernel is issue-slot bound.
+template <int SO>
+__host__ __device__ constexpr int hh_copies() { return (Y2_TC2_HH_COPIES != 0 && SO >= 14 && SO <= 16) ? 1 << (16 - SO) : 1; }
+
 template <int SO>
 __device__ __forceinline__ int tc2_step(int acc, int hh, int mm, int ll)
 {
     int d;
-    if constexpr (SO <= 16) {
+    if constexpr (SO <= 16 && hh_copies<SO>() == (1 << (16 - SO))) {
+        const int t = mm * 256 + ll;                       // IMAD
+        d = hh + (t >> SO);                                // LEA.HI.SX32 (hh arrives pre-scaled)
+    } else if constexpr (SO <= 16) {
         const int t = mm * 256 + ll;                       // IMAD
         d = hh * (1 << (16 - SO)) + (t >> SO);             // IMAD/SHL + LEA.HI.SX32
     } else {
@@ -476,6 +487,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                         const unsigned long long dBh = dB0 + r * kBStep, dBl = dBh + kBPlane;
                         const unsigned d0 = tmem + tb * kBufCols;
                         umma_i8_ts(d0, ah, dBh, idesc_i8(1, 1), 0);            // HH
+#pragma unroll
+                        for (int cpy = 1; cpy < hh_copies<SO>(); ++cpy) umma_i8_ts(d0, ah, dBh, idesc_i8(1, 1), 1);   // ... x 2^(16-so), exact in int32
                         umma_i8_ts(d0 + kN, ah, dBl, idesc_i8(1, 0), 0);       // M  = hi*lo
                         umma_i8_ts(d0 + kN, al, dBh, idesc_i8(0, 1), 1);       //    + lo*hi
                         if constexpr (!kLLCuda) umma_i8_ts(d0 + 2 * kN, al, dBl, idesc_i8(0, 0), 0);   // LL
