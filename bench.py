@@ -263,8 +263,9 @@ def main():
                 "exact_steps_per_s": dom_steps * last_chunk / (dom_ms * 1e-3),
                 "exact_steps_per_s_all_conv": conv_steps * last_chunk / (conv_ms * 1e-3),
                 "note": "the reference rounds+saturates every 4 MACs (Tn=4), so the bit-exact datapath is bound by the CUDA-core "
-                        "round-and-saturate step (4 SASS instr per step behind the tensor cores: 8.2 T steps/s measured in isolation, "
-                        "7 instr / 4.65 T without them) and by the TMEM hand-off latency, not by the tensor pipe; see DESIGN.md and "
+                        "round-and-saturate step (3 SASS instr per step behind the tensor cores for so = 14..16, 4 otherwise; 7 instr / 4.65 T "
+                        "without them): the kernel is bound by the issue slots of the SM sub-partitions (80 % busy in ncu) and the TMEM "
+                        "hand-off round trip, not by the tensor pipe; see DESIGN.md section 4 and "
                         "profiles/.  A reference built with Tn=32 runs at ~2.9 k frames/s on the Tn=32 variant of the same kernel "
                         "(profiles/r1_layer_table_int16_b256_tn32.json)"}
 

@@ -47,15 +47,8 @@ constexpr int kBufs = kLLCuda ? 7 : 5;   // TMEM accumulator buffers: HH | M [| 
 #ifndef Y2_TC2_GROUPS
 #define Y2_TC2_GROUPS 4
 #endif
-#ifndef Y2_TC2_PACKED
-#define Y2_TC2_PACKED 0
-#endif
-// Y2_TC2_PACKED: the three planes of a tile sit at a stride of 28 columns (an N=32 MMA also writes four dead columns, slot 7: each
-// plane's MMAs are issued after the previous plane's and overwrite its dead columns, the last plane's fall into 4 pad columns), so a tile
-// is 84 contiguous live columns and is read out with three loads (x64, x16, x4) instead of nine
-constexpr bool kPacked = Y2_TC2_PACKED != 0 && !kLLCuda && Y2_TC2_GROUPS != 3;
-constexpr int kPlaneCols = kPacked ? kSteps * kPx : kN;
-constexpr int kBufCols = kPacked ? 3 * kPlaneCols + 4 : kPlanes * kN;
+constexpr int kPlaneCols = kN;
+constexpr int kBufCols = kPlanes * kN;
 constexpr int kACol = kBufs * kBufCols;   // 480 / 448: two weight slots of 16 columns (hi plane 8 | lo plane 8)
 constexpr int kXlBytes = kLLCuda ? 2 * 12 * 128 : 0;   // compact copy of the lo activation bytes for the CUDA-core LL: [K-block parity][tile][step][pixel] words
 constexpr int kBRing = 12;          // activation tile ring (hi 1 KB | lo 1 KB) = the kR tiles of one K-block (see the go[] comment in the kernel)
@@ -241,28 +234,6 @@ __device__ __forceinline__ void tmem_ld28(unsigned taddr, int *r)
           "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27])
         : "r"(taddr));
 }
-// 84 contiguous columns (packed planes) with three loads from one address operand
-__device__ __forceinline__ void tmem_ld84(unsigned taddr, int *r)
-{
-    asm volatile(
-        "{\n\t.reg .b32 a1, a2;\n\t"
-        "add.u32 a1, %84, 64;\n\t"
-        "add.u32 a2, %84, 80;\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
-        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%84];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%64,%65,%66,%67,%68,%69,%70,%71,%72,%73,%74,%75,%76,%77,%78,%79}, [a1];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%80,%81,%82,%83}, [a2];\n\t}"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
-          "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
-          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]),
-          "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]),
-          "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63]), "=r"(r[64]), "=r"(r[65]), "=r"(r[66]), "=r"(r[67]), "=r"(r[68]), "=r"(r[69]),
-          "=r"(r[70]), "=r"(r[71]), "=r"(r[72]), "=r"(r[73]), "=r"(r[74]), "=r"(r[75]), "=r"(r[76]), "=r"(r[77]), "=r"(r[78]), "=r"(r[79]),
-          "=r"(r[80]), "=r"(r[81]), "=r"(r[82]), "=r"(r[83])
-        : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_st8(unsigned taddr, const uint4 &a, const uint4 &b)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(a.x), "r"(a.y), "r"(a.z),
@@ -281,7 +252,6 @@ __device__ __forceinline__ void reg_fence12(int *r)
     asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
                    "+r"(r[10]), "+r"(r[11])::"memory");
 }
-__device__ __forceinline__ void reg_fence28(int *r) { reg_fence16(r); reg_fence12(r + 16); }
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
@@ -705,13 +675,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                     tmem_ld16(base + kN, mm); tmem_ld8(base + kN + 16, mm + 16); tmem_ld4(base + kN + 24, mm + 24);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     reg_fence16(hh); reg_fence12(hh + 16); reg_fence16(mm); reg_fence12(mm + 16);
-                } else if constexpr (kPacked) {         // 84 contiguous live columns
-                    int t84[84];
-                    tmem_ld84(base, t84);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    reg_fence28(t84); reg_fence28(t84 + 28); reg_fence28(t84 + 56);
-#pragma unroll
-                    for (int n = 0; n < 28; ++n) { hh[n] = t84[n]; mm[n] = t84[28 + n]; ll[n] = t84[56 + n]; }
                 } else if constexpr (kUShared) {        // only the 28 live columns: 84 registers
                     tmem_ld28(base, hh);
                     tmem_ld28(base + kN, mm);
