@@ -22,6 +22,13 @@
 //    and for 17 <= so <= 22:  c = 256*HH + M; c += LL >> 8; a = acc + (c >> (so-8)); clamp.
 //    Measured issue cost (profiles/microbench/tc_epilogue_rates.cu): 4.55 cycles per warp-step per SMSP
 //    against 6.27 for the 5-instruction scaled step of v1 and ~9.9 for the CUDA-core kernel.
+//  * (end of round 1) the kernel turned out to be bound by the ISSUE SLOTS of the SM sub-partitions (ncu: 80 % busy, 4 of 7 executed
+//    instructions useful), so the instruction count was cut: warp-uniform role / TMEM addressing (shuffle-broadcast warp index),
+//    one address operand per plane read-out, predicated barrier arrives, and for so = 14..16 a THREE-instruction step - the HH
+//    product is issued 2^(16-so) times into its accumulator, TMEM delivers HH*2^(16-so), and  a = HHs + (t >> so)  is one
+//    LEA.HI.SX32.  4.17 -> 5.03 T steps/s on the 13x13x1024 layers; DESIGN.md section 4, profiles/r1_tc2_handoff_experiments.md.
+//  * four epilogue groups (chain state in shared memory between tiles) and a read-out handshake (rd_done[]) that makes the barrier
+//    ring phase-safe: no barrier can complete a second phase before every waiter has tested the first.
 #include "common.cuh"
 #include <cstdio>
 
