@@ -19,7 +19,17 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line (NCCL prints its version banner there otherwise)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout must carry exactly ONE JSON line, but NCCL (and anything else native) writes its banner to file descriptor 1 when the first
+# communicator is created.  Keep a private copy of the real stdout for the result line and point fd 1 at stderr for everything else.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_result(line):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
+
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "yolo-fpga-accelerator_b200"))
 
@@ -134,7 +144,7 @@ def run_reference_arm(args):
             "config": {"workload": "YOLOv2 COCO 416x416 INT16, reference CPU path (--backend hls) on host cores"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_result(line)
     return 0
 
 
@@ -309,7 +319,7 @@ def main():
                 "cpu_baseline": cpu_baseline, "ms_per_step_wall": ms_wall / K,
                 "fps_per_gpu": value / world, "exact_steps_per_s_per_gpu": value / world * STEPS_PER_FRAME,
                 "int8_tensor_equiv_frac": value / world * INT8_OP_PER_FRAME / (int8_peak_tops * 1e12)}
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     y.close()
     if world > 1:
         dist.destroy_process_group()
