@@ -154,3 +154,20 @@ def test_detections_jsonl_format():
     assert d["bbox_px"] == {"x0": int((f(0.5) - f(0.2) * f(0.5)) * f(640)), "y0": int((f(0.5) - f(0.4) * f(0.5)) * f(480)),
                             "x1": int((f(0.5) + f(0.2) * f(0.5)) * f(640)), "y1": int((f(0.5) + f(0.4) * f(0.5)) * f(480))}
     assert d["bbox_px"]["x0"] == 256
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py contract: stdout is exactly ONE JSON line (native banners such as NCCL's go to stderr through the fd redirection);
+    checked on the CPU-only reference arm with a tiny sample."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-procs", "1"], capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port")
