@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--frames-per-gpu", type=int, default=728)
     ap.add_argument("--chunk", type=int, default=0, help="frames per device pass; 0 = the wave-filling size from model.best_pass_size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the region-tensor check against the checker after the timed region")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes for the cpu_baseline leg (default min(cores,32))")
     args = ap.parse_args()
@@ -286,6 +287,33 @@ def main():
     frame_bytes = net.c * net.h * net.w * 4
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * y.region_outputs * 4}
 
+    # ---- parity self-check of the benched configuration at its own size: region tensors of the step against the checker ----
+    # frames: first, the two either side of the device-pass boundary (48-pixel tiles straddle frames inside a pass; the
+    # boundary pair sits in different passes), last.  Both legs are checked: the resident step's device buffer and the
+    # end-to-end step's host buffer.  One GPU: the unmodified reference (oracle/_ref) when it was built; several ranks: two
+    # frames per rank through the C restatement so the host cores are not oversubscribed.
+    parity = None
+    if not args.no_parity_check:
+        from oracle.ref_driver import reference_frames
+        mb = y.max_batch
+        pos = sorted({0, min(mb - 1, B - 1), min(mb, B - 1), B - 1}) if world == 1 else sorted({min(mb - 1, B - 1), min(mb, B - 1)})
+        cores = os.cpu_count() or 1
+        if world > 1:
+            os.environ["OMP_NUM_THREADS"] = str(max(1, cores // (2 * world)))
+        want, kind = reference_frames(cfg_text(), "int16", 0, "default", 1000 + 8 * rank, sorted({q % 8 for q in pos}),
+                                      keep_layers=False, procs=4 if world == 1 else 2)
+        got_dev = dev_region.cpu().numpy()
+        got_host = host_region.numpy()
+        bad = 0
+        for q in pos:
+            w = want[q % 8][0].view(np.uint32)
+            bad += int(not np.array_equal(got_dev[q].view(np.uint32), w)) + int(not np.array_equal(got_host[q].view(np.uint32), w))
+        tot = torch.tensor([bad, len(pos)], device="cuda", dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(tot)
+        parity = {"frames": int(tot[1]), "mismatches": int(tot[0]), "checker": kind, "positions_rank0": pos,
+                  "what": "region tensor of the resident step (device) and of the end-to-end step (host), bit for bit"}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
@@ -317,12 +345,16 @@ def main():
                            "weights": "seeded synthetic int16, Qw=14 Qb=10 Qa=10"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "ms_per_step_wall": ms_wall / K,
+                "parity_checked": parity["frames"] if parity else 0, "parity": parity,
                 "fps_per_gpu": value / world, "exact_steps_per_s_per_gpu": value / world * STEPS_PER_FRAME,
                 "int8_tensor_equiv_frac": value / world * INT8_OP_PER_FRAME / (int8_peak_tops * 1e12)}
         emit_result(line)
     y.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity and parity["mismatches"]:
+        sys.stderr.write(f"bench.py: PARITY FAILURE - {parity['mismatches']} region tensors differ from the checker\n")
+        return 3
     return 0
 
 

@@ -168,6 +168,9 @@ uint64_t yolo2cuda_net_launches_per_forward(const yolo2cuda_net *net);
 int yolo2cuda_net_set_debug_keep(yolo2cuda_net *net, int keep);
 /* Per-layer device time in ms of the last forward (CUDA events; enables them on first use). */
 int yolo2cuda_net_layer_times(yolo2cuda_net *net, float *ms, int n_layers);
+/* Name of the kernel variant the last forward launched for `layer` ("" for layers that launch nothing, e.g. route;
+ * never NULL).  Diagnostics / tests: lets a parity test assert WHICH conv kernel produced the bits it compared. */
+const char *yolo2cuda_net_layer_kernel(const yolo2cuda_net *net, int layer);
 
 /* ---- detections: get_network_boxes + do_nms_sort on the host (src/core/yolo_region.cpp:169-236,
  * src/core/yolo_post.cpp:54-85).  region: one frame's region tensor (HOST).  Outputs hold

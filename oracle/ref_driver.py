@@ -134,3 +134,38 @@ def time_reference_cpu(cfg_text, precision="int16", procs=1, frames_per_proc=1, 
     wall = time.perf_counter() - t0
     worst = max(secs)
     return procs * frames_per_proc / worst, sum(secs) / (procs * frames_per_proc), wall
+
+
+def _frame_worker(job):
+    """one frame (per-layer ofm kept) through the real YOLO2_FPGA, or through the pinned C restatement when oracle/_ref was not built"""
+    cfg_text, precision, pack_seed, table, frame_seed, index, use_ref, keep = job
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "yolo-fpga-accelerator_b200"))
+    from yolo2_b200 import cfg as ycfg, weights as yw
+    from .oracle import Ref
+    net = ycfg.parse_network_cfg(cfg_text)
+    pack = yw.synth_pack(net, precision, seed=pack_seed, table=table)
+    frame = np.random.default_rng(frame_seed + index).random((net.c, net.h, net.w), dtype=np.float32)   # == synth_frames(...)[index]
+    if use_ref:
+        region, dumps, _ = ref_net_forward(Ref(precision), net, frame, pack, keep_layers=keep, helper=Oracle())
+    else:
+        region, dumps = Oracle().net_forward(net, frame, pack, dump_layers=keep)
+    return index, np.asarray(region, np.float32).reshape(-1), dumps
+
+
+def reference_frames(cfg_text, precision, pack_seed, table, frame_seed, indices, keep_layers=True, procs=0):
+    """Frames `indices` of yolo2_b200.weights.synth_frames(net, *, frame_seed) through the checker, one process per frame.
+    Returns ({index: (region flat float32, {layer: ofm})}, "reference" | "port")."""
+    import multiprocessing as mp
+    import os
+    from .oracle import have_ref
+    use_ref = have_ref(precision)
+    jobs = [(cfg_text, precision, pack_seed, table, frame_seed, int(i), use_ref, keep_layers) for i in indices]
+    n = max(1, min(len(jobs), procs or (os.cpu_count() or 1)))
+    if not use_ref:
+        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // n)))
+    with mp.get_context("spawn").Pool(n) as pool:
+        res = pool.map(_frame_worker, jobs)
+    return {i: (region, dumps) for i, region, dumps in res}, ("reference" if use_ref else "port")

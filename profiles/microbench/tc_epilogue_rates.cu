@@ -7,6 +7,9 @@
 //   mode 3: IMAD.HI x4 (is the high-half multiply full rate?)
 //   mode 4: 4-instr general step  IMAD c=256HH+M, LEA.HI c+=(LL>>8), IMAD.HI acc+=(c>>k), VIMNMX.RELU      (2 FMA(1 HI) + 2 ALU)
 //   mode 5: float step            FFMA.RM, FADD, FFMA.RM.SAT, FMNMX                                        (3 FMA + 1 ALU)
+//   mode 6: no-saturation fast step   IMAD t=256M+LL, LEA.HI acc+=(t>>so)                                  (1 FMA + 1 ALU)   [round 2]
+//   mode 7: same with the recombination on the ALU pipe   LEA t=LL+(M<<8), LEA.HI acc+=(t>>so)             (2 ALU)
+//   mode 8: fast step + per-7-step range check (IADD, ISETP.LE.U32 and-chained, one VOTE per 28 steps)
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -60,12 +63,27 @@ __global__ void __launch_bounds__(256) k(int *out, int a0, int b0, int so_rt, lo
                 c = c + (ll[i] >> 8);
                 int a = madhi(c, himul, acc[i]);
                 acc[i] = __vimin_s32_relu(a, 65535);
+            } else if (MODE == 6) {
+                int t = mad(mm[i], 256, ll[i]);
+                acc[i] += t >> so;
+            } else if (MODE == 7) {
+                int t = ll[i] + (mm[i] << 8);
+                acc[i] += t >> so;
+            } else if (MODE == 8) {
+                int t = mad(mm[i], 256, ll[i]);
+                acc[i] += t >> so;
             } else if (MODE == 5) {
                 float q = fma_rm(__int_as_float(ll[i]), s10, C);
                 float t = fadd(__int_as_float(hh[i]), q);
                 float s = fma_rm_sat(t, sk, facc[i]);
                 facc[i] = fminf(s, 0.99998474f);
             }
+        }
+        if (MODE == 8 && (it % 7) == 6) {     // one range check per chain per 7 steps; a failing warp would take the exact path
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) ok = ok && (unsigned)(acc[i] - hmul) <= (unsigned)ubound;
+            if (!__all_sync(0xffffffffu, ok)) { acc[0] ^= 1; }
         }
 #pragma unroll
         for (int i = 0; i < NCH; ++i) asm volatile("" : "+r"(hh[i]), "+r"(mm[i]), "+r"(ll[i]));   // opaque: new partial sums every step
@@ -111,6 +129,9 @@ int main(int argc, char **argv)
         run<3>("IMAD.HI x4", 4, nsm, occ, out, cyc, REP);
         run<4>("tc step v3 (general): IMAD, LEA.HI, IMAD.HI, VIMNMX.RELU", 4, nsm, occ, out, cyc, REP);
         run<5>("float step: FFMA.RM, FADD, FFMA.RM.SAT, FMNMX", 4, nsm, occ, out, cyc, REP);
+        run<6>("fast step (no saturation possible): IMAD, LEA.HI", 2, nsm, occ, out, cyc, REP);
+        run<7>("fast step, ALU only: LEA, LEA.HI", 2, nsm, occ, out, cyc, REP);
+        run<8>("fast step + range check per 7 steps", 2, nsm, occ, out, cyc, REP);
     }
     return cudaDeviceSynchronize() != cudaSuccess;
 }

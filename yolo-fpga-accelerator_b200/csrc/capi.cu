@@ -27,8 +27,8 @@ struct yolo2cuda_ctx {
     const char *last_kernel = "";
     int force_generic = 0;
     int Tn = YOLO2CUDA_Tn, Tm = YOLO2CUDA_Tm;   // tile parameters of the emulated reference build (yolo2cuda_set_tile_params)
-    int use_tc = -1;  // YOLO2CUDA_TC: unset = auto (network executor uses csrc/conv_i16_tc2.cu on the layers where it is faster),
-                      // 0 = CUDA-core kernels only, 1 = csrc/conv_i16_tc.cu, 2 = csrc/conv_i16_tc2.cu wherever eligible
+    int use_tc = -1;  // YOLO2CUDA_TC: unset = auto (the tcgen05 kernel csrc/conv_i16_tc2.cu on the layers where it measured faster),
+                      // 0 = CUDA-core kernels only, anything else = the tcgen05 kernel wherever the shape is eligible (tests / profiling)
     int tc_min_ofm = 96;
     // growable device scratch for the per-layer entry points
     struct Scratch { void *p = nullptr; size_t bytes = 0; } s_in, s_out, s_w, s_b, s_c4in, s_c4out, s_wprep;
@@ -160,16 +160,14 @@ int run_conv_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, cons
     if ((rc = ensure(ctx, ctx->s_c4in, c4_elems(IFM, Ih, Iw) * ctx->elem))) return rc;
     if ((rc = ensure(ctx, ctx->s_c4out, c4_elems(OFM, Oh, Ow) * ctx->elem))) return rc;
     const bool tc = ctx->use_tc > 0 && ctx->elem == 2 && so >= 8 && so <= 22;   // (auto mode: single-frame calls stay on the CUDA cores)
-    const bool tc2 = tc && ctx->use_tc == 2;
-    if ((rc = ensure(ctx, ctx->s_wprep, tc2 ? wprep_tc2_bytes(IFM, OFM, K) : tc ? wprep_tc_bytes(IFM, OFM, K) : wprep_bytes(IFM, OFM, K, ctx->elem)))) return rc;
+    if ((rc = ensure(ctx, ctx->s_wprep, tc ? wprep_tc2_bytes(IFM, OFM, K) : wprep_bytes(IFM, OFM, K, ctx->elem)))) return rc;
     launch_planar_to_c4(Input, ctx->s_c4in.p, 1, IFM, Ih, Iw, 0, 0, ctx->elem, st);
     if (tc) {
-        if (tc2) launch_wprep_tc2((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, so, st);
-        else launch_wprep_tc((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, so, st);
+        launch_wprep_tc2((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, so, st);
         p.in = ctx->s_c4in.p; p.out = ctx->s_c4out.p; p.w = ctx->s_wprep.p; p.bias = Beta;
         p.in_frame_stride = 0; p.out_frame_stride = 0;
         p.so = so; p.sb = sb; p.leaky = IsNL;
-        if ((tc2 ? launch_conv_i16_tc2(p, K, st, &ctx->last_kernel) : launch_conv_i16_tc(p, K, st, &ctx->last_kernel)) < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "tc conv not eligible");
+        if (launch_conv_i16_tc2(p, K, st, &ctx->last_kernel) < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "tc conv not eligible");
         launch_c4_to_planar(ctx->s_c4out.p, Output, 1, OFM, Oh, Ow, 0, 0, ctx->elem, st);
         ctx->launches += 4;
         CUDA_OK(ctx, cudaGetLastError());
@@ -221,7 +219,7 @@ int yolo2cuda_create(yolo2cuda_ctx **out, int device, int precision)
     const char *fg = getenv("YOLO2CUDA_FORCE_GENERIC");
     ctx->force_generic = (fg && fg[0] && fg[0] != '0') ? 1 : 0;
     const char *tc = getenv("YOLO2CUDA_TC");
-    ctx->use_tc = (tc && tc[0]) ? (tc[0] == '0' ? 0 : tc[0] == '2' ? 2 : 1) : -1;
+    ctx->use_tc = (tc && tc[0]) ? (tc[0] == '0' ? 0 : 2) : -1;
     if (const char *mo = getenv("YOLO2CUDA_TC_MIN_OFM")) ctx->tc_min_ofm = atoi(mo);
     *out = ctx;
     return YOLO2CUDA_SUCCESS;
@@ -508,7 +506,7 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
                 int n;
                 if (l.tc) {
                     p.w = l.w_tc;
-                    n = ctx->use_tc != 1 ? launch_conv_i16_tc2(p, l.d.size, st, &l.variant) : launch_conv_i16_tc(p, l.d.size, st, &l.variant);
+                    n = launch_conv_i16_tc2(p, l.d.size, st, &l.variant);
                 } else {
                     n = e == 2 ? launch_conv_i16_fast(p, l.d.size, st, &l.variant) : launch_conv_f32_fast(p, l.d.size, st, &l.variant);
                 }
@@ -535,18 +533,20 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
                                         l.d.out_c, l.d.out_h, l.d.out_w, 0, 0, e, st);
                     launches += 3;
                 }
-                ctx->last_kernel = e == 2 ? "conv_i16_generic" : "conv_f32_generic";
+                ctx->last_kernel = l.variant = e == 2 ? "conv_i16_generic" : "conv_f32_generic";
             }
             break;
         }
         case YOLO2CUDA_MAXPOOL:
             launch_maxpool_c4(l.in.base, l.out.base, B, ceil_div(l.d.c, 4), l.d.stride, l.d.w, l.d.h, l.d.out_w, l.d.out_h,
                               l.in.frame_stride, l.out.frame_stride, e, st);
+            l.variant = "maxpool_c4";
             ++launches;
             break;
         case YOLO2CUDA_REORG:
             launch_reorg_driver_c4(l.in.base, l.out.base, B, l.d.c, l.d.h, l.d.w, l.reorg_shift, l.in.frame_stride,
                                    l.out.frame_stride, e, st);
+            l.variant = "reorg_driver_c4";
             ++launches;
             break;
         case YOLO2CUDA_ROUTE:
@@ -554,6 +554,7 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
         case YOLO2CUDA_REGION:
             launch_region(l.in.base, region_dev, B, l.d.w, l.d.h, l.d.n, l.d.classes, l.d.coords, l.d.softmax,
                           l.d.background, l.region_q, 1, l.in.frame_stride, e, st);
+            l.variant = "region";
             ++launches;
             break;
         default:
@@ -831,10 +832,8 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                          (l.d.size == 1 && l.d.w <= 26 && l.d.n >= 256 && l.d.c >= 512)))
                         l.tc = true;
                     if (l.tc) {
-                        const bool v2 = ctx->use_tc != 1;
-                        if (!l.w_tc && (rc = net_alloc(net, &l.w_tc, v2 ? wprep_tc2_bytes(l.d.c, l.d.n, l.d.size) : wprep_tc_bytes(l.d.c, l.d.n, l.d.size)))) return rc;
-                        if (v2) launch_wprep_tc2((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, so, st);
-                        else launch_wprep_tc((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, so, st);
+                        if (!l.w_tc && (rc = net_alloc(net, &l.w_tc, wprep_tc2_bytes(l.d.c, l.d.n, l.d.size)))) return rc;
+                        launch_wprep_tc2((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, so, st);
                         ctx->launches += 1;
                     }
                 }
@@ -999,6 +998,13 @@ int yolo2cuda_net_set_debug_keep(yolo2cuda_net *net, int keep)
 {
     (void)keep;  // every layer owns its output buffer in this version: nothing to switch
     return net ? YOLO2CUDA_SUCCESS : YOLO2CUDA_ERROR;
+}
+
+const char *yolo2cuda_net_layer_kernel(const yolo2cuda_net *net, int layer)
+{
+    if (!net || layer < 0 || layer >= (int)net->L.size()) return "";
+    const LayerPlan &l = net->L[layer];
+    return l.variant ? l.variant : "";
 }
 
 int yolo2cuda_net_layer_times(yolo2cuda_net *net, float *ms, int n_layers)

@@ -111,11 +111,7 @@ void launch_region(const void *in, float *out, int B, int w, int h, int n, int c
 }  // namespace y2
 
 namespace y2 {
-// tensor-core (tcgen05) int16 conv, csrc/conv_i16_tc.cu
-size_t wprep_tc_bytes(int ifm, int ofm, int ksize);
-void launch_wprep_tc(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, int so, cudaStream_t st);
-int launch_conv_i16_tc(const ConvFastParams &p, int ksize, cudaStream_t st, const char **variant);
-// pipeline v2 (weights in tensor memory, 4-instruction step), csrc/conv_i16_tc2.cu
+// tensor-core (tcgen05 + TMEM) int16 conv, csrc/conv_i16_tc2.cu
 size_t wprep_tc2_bytes(int ifm, int ofm, int ksize);
 void launch_wprep_tc2(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, int so, cudaStream_t st);
 int launch_conv_i16_tc2(const ConvFastParams &p, int ksize, cudaStream_t st, const char **variant);

@@ -109,6 +109,10 @@ class Yolo2Net:
     def launches_per_forward(self):
         return int(self.lib.yolo2cuda_net_launches_per_forward(self.handle))
 
+    def layer_kernel(self, layer: int) -> str:
+        """kernel variant the last forward launched for `layer` ("" for route layers)"""
+        return self.lib.yolo2cuda_net_layer_kernel(self.handle, layer).decode()
+
     def layer_times(self):
         ms = np.zeros(len(self.net.layers), np.float32)
         _capi.check(self.accel.ctx, self.lib.yolo2cuda_net_layer_times(self.handle, ms.ctypes.data_as(C.c_void_p), ms.size))
