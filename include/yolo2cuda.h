@@ -157,15 +157,22 @@ int yolo2cuda_net_forward_images_host(yolo2cuda_net *net, const unsigned char *i
                                       float *region_out);
 
 /* Copies layer `layer`'s output feature map of frame `frame` (from the last forward) to the
- * HOST buffer `dst` in the reference layout [out_c][out_h][ceil8(out_w)] (int16_t or float). */
+ * HOST buffer `dst` in the reference layout [out_c][out_h][ceil8(out_w)] (int16_t or float).
+ * Needs yolo2cuda_net_set_debug_keep(net, 1) BEFORE the forward. */
 int yolo2cuda_net_get_layer_output(yolo2cuda_net *net, int layer, int frame, void *dst, size_t dst_elems);
 /* Activation Q of the tensor entering the region layer after the last forward (int16). */
 int yolo2cuda_net_region_q(const yolo2cuda_net *net);
 /* Kernels launched by one forward of `batch` frames (0 before the first forward). */
 uint64_t yolo2cuda_net_launches_per_forward(const yolo2cuda_net *net);
-/* Keep per-layer outputs distinct so get_layer_output works for every layer (default 0: the
- * arena ping-pongs like the reference's, yolo2_model.cpp:56-110, and only live tensors survive). */
+/* Activation memory.  Default (keep = 0): ONE device arena in which a tensor occupies its bytes only between its first
+ * writer and its last reader, so buffers are recycled down the network like the reference's ping-pong scratch arena
+ * (yolo2_model.cpp:56-110); the route source (layer 16) and the concat buffer stay alive across the layers between their
+ * writers and readers.  keep = 1: every tensor owns its memory, so yolo2cuda_net_get_layer_output works for EVERY layer of
+ * the last forward (tests, per-layer dumps); get_layer_output fails in the default mode.  Switching re-places the tensors
+ * (allowed at any time between forwards; the weights stay loaded). */
 int yolo2cuda_net_set_debug_keep(yolo2cuda_net *net, int keep);
+/* Bytes of device memory the activation tensors occupy in the current mode (arena size, or the sum over layers). */
+size_t yolo2cuda_net_activation_bytes(const yolo2cuda_net *net);
 /* Per-layer device time in ms of the last forward (CUDA events; enables them on first use). */
 int yolo2cuda_net_layer_times(yolo2cuda_net *net, float *ms, int n_layers);
 /* Name of the kernel variant the last forward launched for `layer` ("" for layers that launch nothing, e.g. route;
@@ -173,9 +180,12 @@ int yolo2cuda_net_layer_times(yolo2cuda_net *net, float *ms, int n_layers);
 const char *yolo2cuda_net_layer_kernel(const yolo2cuda_net *net, int layer);
 
 /* ---- detections: get_network_boxes + do_nms_sort on the host (src/core/yolo_region.cpp:169-236,
- * src/core/yolo_post.cpp:54-85).  region: one frame's region tensor (HOST).  Outputs hold
- * w*h*n entries: boxes [..][4] = x,y,w,h relative to the original image; probs [..][classes].
- * Returns the entry count (w*h*n) or a negative YOLO2CUDA_* code. */
+ * src/core/yolo_post.cpp:54-85).  region: one frame's region tensor (HOST).  The output arrays must hold
+ * lw*lh*n entries (the worst case); the function fills the first K of them, K = the number of candidates with
+ * objectness > thresh, in the reference's candidate scan order (cell-major, then anchor - the order of its list before
+ * do_nms_sort's qsort re-orders it), and RETURNS K (or a negative YOLO2CUDA_* code).  boxes [K][4] = x,y,w,h relative to
+ * the original image; probs [K][classes] after per-class NMS (suppressed entries 0); objectness [K].  The set of surviving
+ * (box, class, probability) equals the reference's, including ties (same libc qsort on an order carried across classes). */
 int yolo2cuda_region_detections(const float *region, int lw, int lh, int n, int classes,
                                 const float *anchors, int im_w, int im_h, int net_w, int net_h,
                                 float thresh, float nms, float *boxes, float *probs, float *objectness);

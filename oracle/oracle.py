@@ -38,6 +38,9 @@ def build(ref=True, quiet=True):
     if ref and os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-C", HERE, "ref"], stdout=out)
         subprocess.check_call(["make", "-C", HERE, "ref-variants"], stdout=out)   # the reference built with --tn 8 / 16 / 32
+        if os.path.exists(os.path.join(HERE, "..", "yolo-fpga-accelerator_b200", "lib", "libyolo2cuda.so")):
+            # the reference's own CLI with the `--backend cuda` patch of INTEGRATION.md (tests/test_cli_backend_cuda.py)
+            subprocess.check_call(["make", "-C", HERE, "ref-detect"], stdout=out)
 
 
 def ref_so(precision="int16", tn=4):

@@ -78,6 +78,63 @@ def test_quantize_pack_q_selection_and_layout(thin_net):
     assert convert.best_q(0.0) == 15 and convert.best_q(1.0) == 14 and convert.best_q(40000.0) == 0
 
 
+def _route_entries(net):
+    """table entries tied by `route -9` (source conv output, conv before the route) and ordered by the concat (skip, branch)"""
+    convs = [i for i, l in enumerate(net.layers) if l.type == ycfg.CONV]
+    no = {i: k for k, i in enumerate(convs)}
+    single = next(i for i, l in enumerate(net.layers) if l.type == ycfg.ROUTE and len(l.inputs) == 1)
+    multi = next(i for i, l in enumerate(net.layers) if l.type == ycfg.ROUTE and len(l.inputs) == 2)
+    src = no[net.layers[single].inputs[0]] + 1
+    before_route = no[max(c for c in convs if c < single)] + 1
+    reorg = next(a for a in net.layers[multi].inputs if net.layers[a].type == ycfg.REORG)
+    skip = no[next(b for b in net.layers[multi].inputs if b != reorg)] + 1
+    branch = no[max(c for c in convs if c < reorg)] + 1
+    return src, before_route, skip, branch
+
+
+def test_harmonise_route_q_rules(thin_net):
+    """the driver loop reads Qa_in by table position and only rescales the reorg branch (yolo2_model.cpp:311-336,379-399): the
+    calibrated table must tie the `route -9` entries and keep Q_skip <= Q_branch; everything else stays as calibrated"""
+    src, before_route, skip, branch = _route_entries(thin_net)
+    assert (src, before_route, skip, branch) == (13, 20, 20, 21)       # YOLOv2: conv 12 = layer 16, conv 19 = layer 24, conv 20 = layer 26
+    n = len(thin_net.conv_layers)
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        q = rng.integers(3, 14, n + 1).astype(np.int32)
+        h = convert.harmonise_route_q(thin_net, q)
+        assert h[src] == h[before_route] and h[skip] <= h[branch]
+        assert (h <= q).all()
+        untouched = [k for k in range(n + 1) if k not in (src, before_route, skip)]
+        assert np.array_equal(h[untouched], q[untouched])
+        assert h[src] == min(q[src], q[before_route], q[branch]) or h[src] == min(q[src], q[before_route])
+        assert np.array_equal(convert.harmonise_route_q(thin_net, h), h)     # idempotent
+
+
+@pytest.mark.gpu
+def test_route_q_mismatch_is_harmonised(thin_net, tmp_path):
+    """a model whose skip conv (layer 24) produces much smaller values than the route source (layer 16): the raw calibration
+    gives them different Qs, which the driver loop would mis-read; with the harmonised table the int16 net tracks the fp32 net,
+    with the raw table it does not"""
+    from yolo2_b200.model import Yolo2Net
+    layers = _fake_darknet(thin_net, 9)
+    layers[19].weights *= np.float32(1.0 / 16)            # conv 19 = layer 24
+    layers[19].biases *= np.float32(1.0 / 16)
+    folded = convert.fold_batchnorm(layers)
+    fp32 = convert.make_fp32_pack(thin_net, folded)
+    frames = yw.synth_frames(thin_net, 2, seed=78)
+    raw = convert.calibrate_activation_q(thin_net, fp32, frames, harmonise=False)
+    src, before_route, skip, branch = _route_entries(thin_net)
+    assert raw[src] != raw[before_route]                  # the scenario really has the inconsistency
+    errs = {}
+    for name, table in (("raw", raw), ("harmonised", convert.harmonise_route_q(thin_net, raw))):
+        ya, yb = Yolo2Net(thin_net, fp32, max_batch=2), Yolo2Net(thin_net, convert.quantize_pack(thin_net, folded, table), max_batch=2)
+        try:
+            errs[name] = float(np.abs(ya.forward(frames) - yb.forward(frames)).mean())
+        finally:
+            ya.close(); yb.close()
+    assert errs["harmonised"] < 0.04 and errs["harmonised"] < 0.5 * errs["raw"], errs
+
+
 @pytest.mark.gpu
 def test_darknet_to_int16_end_to_end(thin_net, tmp_path):
     """darknet file -> fold -> fp32 pack -> activation calibration on the CUDA fp32 path -> int16 pack -> files -> reload;

@@ -23,7 +23,10 @@ def _run_case(width, classes, batch, max_batch, precision, table, check_frames, 
     want, _ = reference_frames(cfg_text, precision, pack_seed, table, frame_seed, check_frames)
     y = Yolo2Net(net, pack, max_batch=max_batch)
     try:
+        region_compact = y.forward(frames)              # default: compact arena (what bench.py runs)
+        y.set_debug_keep(True)                          # per-layer dumps need every tensor kept
         region = y.forward(frames)
+        assert np.array_equal(region.view(np.uint32), region_compact.view(np.uint32)), "compact arena and keep-all mode differ"
         kernels = {i: y.layer_kernel(i) for i in range(len(net.layers))}
         last_chunk0 = ((batch - 1) // max_batch) * max_batch           # per-layer dumps exist for the frames of the LAST device pass
         for f in check_frames:

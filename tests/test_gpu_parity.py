@@ -109,7 +109,12 @@ def _net_case(width, height, classes, channel_div, table, seed, precision="int16
 def _check_net(net, pack, frames, oracle, max_batch, tol=None):
     y = Yolo2Net(net, pack, max_batch=max_batch)
     try:
+        region_compact = y.forward(frames)              # default: compact arena, buffers recycled down the network
+        compact_bytes = y.activation_bytes
+        y.set_debug_keep(True)                          # per-layer dumps need every tensor kept
         region = y.forward(frames)
+        assert np.array_equal(region.view(np.uint32), region_compact.view(np.uint32)), "compact arena and keep-all mode differ"
+        assert compact_bytes < y.activation_bytes
         B = frames.shape[0]
         for f in sorted({0, B - 1}):
             if B > max_batch and f == 0:
@@ -471,6 +476,7 @@ def test_whole_net_rounding_group_variant(tn, oracle):
     acc.set_tile_params(tn, 32)
     oracle.set_tile_params(tn, 32)
     y = Yolo2Net(net, pack, max_batch=2, accel=acc)
+    y.set_debug_keep(True)
     try:
         region = y.forward(frames)
         for f in (0, 1):
@@ -561,3 +567,22 @@ def test_detection_stream_end_to_end(oracle):
         assert _det_set(boxes[f], probs[f]) == _det_set(wb, wp)
         rec = json.loads(lines[f])
         assert rec["width"] == 160 and rec["height"] == 120 and rec["frame_index"] == f
+
+
+def test_detection_stream_608_uses_host_tail(oracle):
+    """a 608x608 net has 19*19*5 = 1805 candidates per frame, more than detect_kernel sorts in one CTA: DetectionStream then
+    runs the library's host tail per frame and returns the same positional layout; detection set == the checker's"""
+    from yolo2_b200.app import DetectionStream
+    net, pack = _net_case(608, 608, 3, 8, "default", seed=6)
+    imgs = np.random.default_rng(124).integers(0, 256, (2, 90, 160, 3), dtype=np.uint8)
+    ds = DetectionStream(net, pack, batch=2, thresh=0.05, nms=0.45)
+    try:
+        boxes, probs, obj = ds.detect(imgs)
+    finally:
+        ds.close()
+    l = net.layers[-1]
+    assert boxes.shape == (2, 19 * 19 * 5, 4)
+    for f in range(2):
+        region, _ = oracle.net_forward(net, oracle.letterbox_u8(imgs[f], 608, 608), pack)
+        wb, wp, wo = oracle.region_boxes_nms(region, l.w, l.h, l.n, l.classes, l.anchors, 160, 90, net.w, net.h, 0.05, 0.45)
+        assert _det_set(boxes[f], probs[f]) == _det_set(wb, wp)

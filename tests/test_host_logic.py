@@ -129,6 +129,37 @@ def test_host_detections_match_oracle(oracle):
         assert key(b, p, o) == key(wb[live], wp[live], wo[live])
 
 
+def _tied_region(seed, classes=6, n=5, w=13, h=13):
+    """a post-activation region tensor with MANY equal class probabilities and heavily overlapping boxes: which of two tied,
+    overlapping candidates survives NMS then depends on the order the previous class's qsort left (yolo_post.cpp:70-74)"""
+    rng = np.random.default_rng(seed)
+    r = np.zeros((n, 5 + classes, h, w), np.float32)
+    r[:, 0:2] = 0.5
+    r[:, 2:4] = rng.choice([1.0, 1.25], (n, 2, h, w))                  # exp(.) * anchor / 13: boxes several cells wide
+    r[:, 4] = rng.choice([0.0, 0.5, 0.5, 0.75], (n, h, w))            # objectness: few distinct values
+    r[:, 5:] = rng.choice([0.125, 0.25, 0.5], (n, classes, h, w))     # class probabilities: few distinct values
+    return r
+
+
+def test_host_detections_tie_order_matches_oracle(oracle):
+    """equal scores + overlapping boxes: the carried-over qsort order decides the survivor; host path == checker"""
+    from yolo2_b200.model import region_detections
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 6))
+    l = net.layers[-1]
+    key = lambda bb, pp, oo: sorted((tuple(x.tolist()), float(z), tuple(np.nonzero(q)[0].tolist()), tuple(q[q > 0].tolist()))
+                                    for x, q, z in zip(bb, pp, oo))
+    suppressed = 0
+    for seed in range(4):
+        region = _tied_region(seed)
+        b, p, o = region_detections(net, region, 640, 480, 0.1, 0.45)
+        wb, wp, wo = oracle.region_boxes_nms(region, 13, 13, 5, 6, l.anchors, 640, 480, 416, 416, 0.1, 0.45)
+        live = wo > 0
+        assert len(b) == live.sum() > 100
+        assert key(b, p, o) == key(wb[live], wp[live], wo[live])
+        suppressed += int((p == 0).sum())
+    assert suppressed > 1000          # NMS really decided between tied candidates
+
+
 def test_glibc_expf_restatement_matches_libm(tmp_path):
     """oracle/expf_check.c: the double-arithmetic restatement of glibc's expf that the CUDA detection kernel uses for the box
     width / height equals the host libm's expf (what the reference's std::exp(float) calls) on 2^22 inputs, bit for bit."""

@@ -86,6 +86,20 @@ def test_region_forward_and_boxes_match_reference(oracle, ref16):
         assert np.array_equal(go.view(np.uint32), wo.view(np.uint32))
 
 
+def test_nms_tie_order_matches_reference(oracle, ref16):
+    """equal probabilities and overlapping boxes: do_nms_sort's qsort starts each class from the order the previous class left
+    (src/core/yolo_post.cpp:70-74); the restatement must resolve the ties the same way (same list, same order, same bits)"""
+    from test_host_logic import _tied_region
+    anchors = np.array([0.57273, 0.677385, 1.87446, 2.06253, 3.33843, 5.47434, 7.88282, 3.52778, 9.77052, 9.16828], np.float32)
+    for seed in range(4):
+        region = _tied_region(seed)
+        wb, wp, wo = ref16.region_boxes_nms(region, 13, 13, 5, 6, anchors, 640, 480, 416, 416, 0.1, 0.45)
+        gb, gp, go = oracle.region_boxes_nms(region, 13, 13, 5, 6, anchors, 640, 480, 416, 416, 0.1, 0.45)
+        assert np.array_equal(gb.view(np.uint32), wb.view(np.uint32))
+        assert np.array_equal(gp.view(np.uint32), wp.view(np.uint32))
+        assert np.array_equal(go.view(np.uint32), wo.view(np.uint32))
+
+
 @pytest.mark.slow
 @pytest.mark.parametrize("width,classes,table,precision", [(416, 3, "stress", "int16"), (608, 20, "stress", "int16"),
                                                             (416, 20, "saturate", "int16"), (416, 3, "default", "fp32")])

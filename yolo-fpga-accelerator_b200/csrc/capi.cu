@@ -383,15 +383,16 @@ int yolo2cuda_region_detections_dev(yolo2cuda_ctx *ctx, const float *region, int
     if (batch <= 0 || lw <= 0 || lh <= 0 || n <= 0 || classes <= 0 || im_w <= 0 || im_h <= 0 || net_w <= 0 || net_h <= 0)
         return fail(ctx, YOLO2CUDA_ERROR, "region_detections_dev: bad dimensions");
     CUDA_OK(ctx, cudaSetDevice(ctx->device));
-    // 2^(i/32) correctly rounded: the table of glibc's expf (long double exp2, then one rounding to double)
-    static double tab[32];
-    static bool tab_ready = false;
-    if (!tab_ready) {
-        for (int i = 0; i < 32; ++i) tab[i] = (double)exp2l((long double)i / 32);
-        tab_ready = true;
-    }
+    // 2^(i/32) correctly rounded: the table of glibc's expf (long double exp2, then one rounding to double).  A function-local
+    // static initialised by a lambda: C++11 guarantees one thread builds it and every other caller sees it complete.
+    struct ExpfTable { double v[32]; };
+    static const ExpfTable tab = [] {
+        ExpfTable t;
+        for (int i = 0; i < 32; ++i) t.v[i] = (double)exp2l((long double)i / 32);
+        return t;
+    }();
     if (launch_detect(region, boxes, probs, objectness, batch, lw, lh, n, classes, anchors_host, im_w, im_h, net_w, net_h, thresh, nms,
-                      tab, ctx->stream) < 0)
+                      tab.v, ctx->stream) < 0)
         return fail(ctx, YOLO2CUDA_ERROR, "region_detections_dev: more than 1024 candidates per frame (use yolo2cuda_region_detections)");
     ctx->launches += 1;
     CUDA_OK(ctx, cudaGetLastError());
@@ -431,10 +432,16 @@ struct yolo2cuda_net {
     int max_batch = 0;
     int in_c = 0, in_h = 0, in_w = 0;
     size_t region_outputs = 0;
-    std::vector<void *> owned;     // device allocations
+    std::vector<void *> owned;     // device allocations that live as long as the net (weights, staging, scratch)
+    // activation tensors: [0] = the quantised C4 input, [1 + i] = output of layer i (conv / pool / reorg outside a concat) or the
+    // concat buffer of a multi-input route i.  place_tensors() maps them to device memory.
+    struct Tensor { size_t bytes = 0; int first_def = 1 << 30, last_use = -1; size_t offset = 0; void *own = nullptr; };
+    std::vector<Tensor> T;
+    std::vector<int> concat_of, concat_goff;   // per layer: the route whose concat buffer this layer writes into (-1), and its group offset
+    void *arena = nullptr;         // compact mode: one allocation, tensors at liveness-packed offsets
+    size_t arena_bytes = 0;
+    bool keep_all = false;         // debug mode: every tensor owns its memory, so every layer's ofm survives the forward
     void *d_input_c4 = nullptr;
-    void *d_frames = nullptr;      // staging for forward_host: float [max_batch][c][h][w]
-    void *d_region = nullptr;      // staging for forward_host
     void *d_frames2[2] = {nullptr, nullptr}, *d_region2[2] = {nullptr, nullptr};   // double-buffered staging
     void *d_lb_frames = nullptr, *d_lb_region = nullptr, *d_lb_img = nullptr;       // forward_images_host: letterboxed frames, region, raw u8 images
     size_t lb_img_bytes = 0;
@@ -476,6 +483,101 @@ int find_skip_layer(const std::vector<LayerPlan> &L)
                     for (int b = 0; b < L[i].d.n_inputs; ++b)
                         if (b != a) return L[i].d.inputs[b];
     return -1;
+}
+
+// Maps the activation tensors to device memory and (re)builds every layer's in/out view.
+//   compact (default): ONE arena; a tensor occupies [offset, offset + bytes) only between its first writer and its last reader,
+//     so buffers are recycled down the network like the reference's ping-pong scratch arena (yolo2_model.cpp:56-110) - about a
+//     third of the keep-all footprint for YOLOv2 (the two live tensors of the widest layers instead of all 31).
+//   keep_all: every tensor owns its memory, so yolo2cuda_net_get_layer_output works for every layer after a forward.
+int place_tensors(yolo2cuda_net *net, bool keep_all)
+{
+    yolo2cuda_ctx *ctx = net->ctx;
+    const int e = ctx->elem;
+    cudaStreamSynchronize(ctx->stream);
+    if (net->arena) { cudaFree(net->arena); net->arena = nullptr; net->arena_bytes = 0; }
+    for (auto &t : net->T)
+        if (t.own) { cudaFree(t.own); t.own = nullptr; }
+    net->keep_all = keep_all;
+    auto base_of = [&](int t) -> char * { return keep_all ? (char *)net->T[t].own : (char *)net->arena + net->T[t].offset; };
+    if (keep_all) {
+        for (auto &t : net->T)
+            if (t.bytes) {
+                CUDA_OK(ctx, cudaMalloc(&t.own, t.bytes));
+                CUDA_OK(ctx, cudaMemsetAsync(t.own, 0, t.bytes, ctx->stream));
+            }
+    } else {
+        // first-fit by address over the tensors in order of their first writer; two tensors may share bytes only when their
+        // [first_def, last_use] layer intervals are disjoint (closed intervals: a layer's input and output never overlap)
+        std::vector<int> order;
+        for (int t = 0; t < (int)net->T.size(); ++t)
+            if (net->T[t].bytes) order.push_back(t);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return net->T[a].first_def < net->T[b].first_def; });
+        std::vector<int> placed;
+        size_t top = 0;
+        for (int t : order) {
+            auto &x = net->T[t];
+            const size_t need = (x.bytes + 1023) & ~(size_t)1023;
+            std::vector<std::pair<size_t, size_t>> busy;       // [begin, end) of the placed tensors alive at the same time
+            for (int u : placed) {
+                const auto &y = net->T[u];
+                if (y.first_def <= x.last_use && x.first_def <= y.last_use) busy.emplace_back(y.offset, y.offset + ((y.bytes + 1023) & ~(size_t)1023));
+            }
+            std::sort(busy.begin(), busy.end());
+            size_t at = 0;
+            for (auto &b : busy) {
+                if (at + need <= b.first) break;
+                at = std::max(at, b.second);
+            }
+            x.offset = at;
+            top = std::max(top, at + need);
+            placed.push_back(t);
+        }
+        net->arena_bytes = top;
+        CUDA_OK(ctx, cudaMalloc(&net->arena, top ? top : 16));
+        CUDA_OK(ctx, cudaMemsetAsync(net->arena, 0, top ? top : 16, ctx->stream));
+    }
+    // ---- views ------------------------------------------------------------------------------------
+    const int n_layers = (int)net->L.size();
+    net->d_input_c4 = base_of(0);
+    for (int i = 0; i < n_layers; ++i) {
+        LayerPlan &l = net->L[i];
+        const yolo2cuda_layer_desc &d = l.d;
+        if (i == 0) {
+            l.in.base = net->d_input_c4;
+            l.in.frame_stride = (long long)c4_elems(net->in_c, net->in_h, net->in_w);
+            l.in.C = net->in_c; l.in.H = net->in_h; l.in.W = net->in_w;
+        } else if (d.type != YOLO2CUDA_ROUTE) {
+            l.in = net->L[i - 1].out;
+        }
+        if (d.type == YOLO2CUDA_ROUTE) {
+            if (d.n_inputs == 1) {
+                l.out = net->L[d.inputs[0]].out;
+            } else {
+                l.out.base = base_of(1 + i);
+                l.out.frame_stride = (long long)c4_elems(d.out_c, d.out_h, d.out_w);
+                l.out.C = d.out_c; l.out.H = d.out_h; l.out.W = d.out_w;
+            }
+        } else if (d.type == YOLO2CUDA_REGION) {
+            l.out = TensorView{};
+        } else {
+            l.out.C = d.out_c; l.out.H = d.out_h; l.out.W = d.out_w;
+            const int co = net->concat_of[i];
+            if (co >= 0) {
+                const yolo2cuda_layer_desc &cd = net->L[co].d;
+                l.out.frame_stride = (long long)c4_elems(cd.out_c, cd.out_h, cd.out_w);
+                l.out.base = base_of(1 + co) + (size_t)net->concat_goff[i] * d.out_h * d.out_w * 4 * e;
+            } else {
+                l.out.base = base_of(1 + i);
+                l.out.frame_stride = (long long)c4_elems(d.out_c, d.out_h, d.out_w);
+            }
+        }
+        // launch parameters prepared by net_load_weights point into the tensors
+        l.cp.in = l.in.base; l.cp.out = l.out.base;
+        l.cp.in_frame_stride = l.in.frame_stride; l.cp.out_frame_stride = l.out.frame_stride;
+    }
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return YOLO2CUDA_SUCCESS;
 }
 
 int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *region_dev)
@@ -639,64 +741,52 @@ int yolo2cuda_net_create(yolo2cuda_ctx *ctx, const yolo2cuda_layer_desc *layers,
     }
 
     int rc;
-    if ((rc = net_alloc(net, &net->d_input_c4, c4_elems(net->in_c, net->in_h, net->in_w) * (size_t)max_batch * e))) {
-        yolo2cuda_net_destroy(net);
-        return rc;
-    }
+    // ---- tensor table + lifetimes (first writer .. last reader, in layer order) ------------------
+    net->concat_of = concat_of;
+    net->concat_goff = concat_goff;
+    net->T.assign(1 + n_layers, yolo2cuda_net::Tensor{});
+    net->T[0].bytes = c4_elems(net->in_c, net->in_h, net->in_w) * (size_t)max_batch * e;
+    net->T[0].first_def = -1;
     size_t max_planar = planar_elems(net->in_c, net->in_h, net->in_w);
-    std::vector<void *> concat_buf(n_layers, nullptr);
-    for (int i = 0; i < n_layers; ++i) {  // allocate concat buffers first
-        const yolo2cuda_layer_desc &d = layers[i];
-        if (d.type == YOLO2CUDA_ROUTE && d.n_inputs >= 2) {
-            if ((rc = net_alloc(net, &concat_buf[i], c4_elems(d.out_c, d.out_h, d.out_w) * (size_t)max_batch * e))) {
-                yolo2cuda_net_destroy(net);
-                return rc;
-            }
-        }
-    }
+    std::vector<int> tensor_of(n_layers, -1);      // tensor a layer's OUTPUT view lives in
+    int prev_tensor = 0;                           // tensor the next non-route layer reads
     for (int i = 0; i < n_layers; ++i) {
-        LayerPlan &l = net->L[i];
-        const yolo2cuda_layer_desc &d = l.d;
-        // input view
-        if (i == 0) {
-            l.in.base = net->d_input_c4;
-            l.in.frame_stride = (long long)c4_elems(net->in_c, net->in_h, net->in_w);
-            l.in.C = net->in_c; l.in.H = net->in_h; l.in.W = net->in_w;
-        } else if (d.type != YOLO2CUDA_ROUTE) {
-            l.in = net->L[i - 1].out;
-            if (l.in.C != d.c || l.in.H != d.h || l.in.W != d.w)
-                NET_FAIL("layer %d: input dims %dx%dx%d do not match the previous output %dx%dx%d", i, d.c, d.h, d.w, l.in.C, l.in.H, l.in.W);
-        }
-        // output view
+        const yolo2cuda_layer_desc &d = layers[i];
+        auto touch_read = [&](int t) { if (t >= 0) net->T[t].last_use = std::max(net->T[t].last_use, i); };
         if (d.type == YOLO2CUDA_ROUTE) {
             if (d.n_inputs == 1) {
-                l.out = net->L[d.inputs[0]].out;
+                tensor_of[i] = tensor_of[d.inputs[0]];
             } else {
-                l.out.base = concat_buf[i];
-                l.out.frame_stride = (long long)c4_elems(d.out_c, d.out_h, d.out_w);
-                l.out.C = d.out_c; l.out.H = d.out_h; l.out.W = d.out_w;
-            }
-        } else if (d.type == YOLO2CUDA_REGION) {
-            l.out = TensorView{};
-            net->region_outputs = (size_t)d.c * d.h * d.w;
-        } else {
-            l.out.C = d.out_c; l.out.H = d.out_h; l.out.W = d.out_w;
-            if (concat_of[i] >= 0) {
-                const yolo2cuda_layer_desc &cd = layers[concat_of[i]];
-                l.out.frame_stride = (long long)c4_elems(cd.out_c, cd.out_h, cd.out_w);
-                l.out.base = (char *)concat_buf[concat_of[i]] + (size_t)concat_goff[i] * d.out_h * d.out_w * 4 * e;
-            } else {
-                void *p = nullptr;
-                if ((rc = net_alloc(net, &p, c4_elems(d.out_c, d.out_h, d.out_w) * (size_t)max_batch * e))) {
-                    yolo2cuda_net_destroy(net);
-                    return rc;
-                }
-                l.out.base = p;
-                l.out.frame_stride = (long long)c4_elems(d.out_c, d.out_h, d.out_w);
+                tensor_of[i] = 1 + i;
+                net->T[1 + i].bytes = c4_elems(d.out_c, d.out_h, d.out_w) * (size_t)max_batch * e;
             }
             max_planar = std::max(max_planar, planar_elems(d.out_c, d.out_h, d.out_w));
+        } else {
+            if (i > 0 && (layers[i - 1].out_c != d.c || layers[i - 1].out_h != d.h || layers[i - 1].out_w != d.w))
+                NET_FAIL("layer %d: input dims %dx%dx%d do not match the previous output %dx%dx%d", i, d.c, d.h, d.w,
+                         layers[i - 1].out_c, layers[i - 1].out_h, layers[i - 1].out_w);
+            touch_read(prev_tensor);
+            if (d.type == YOLO2CUDA_REGION) {
+                net->region_outputs = (size_t)d.c * d.h * d.w;
+            } else {
+                const int t = concat_of[i] >= 0 ? 1 + concat_of[i] : 1 + i;
+                tensor_of[i] = t;
+                if (concat_of[i] < 0) net->T[t].bytes = c4_elems(d.out_c, d.out_h, d.out_w) * (size_t)max_batch * e;
+                net->T[t].first_def = std::min(net->T[t].first_def, i);
+                max_planar = std::max(max_planar, planar_elems(d.out_c, d.out_h, d.out_w));
+            }
         }
-        if (d.type == YOLO2CUDA_ROUTE) max_planar = std::max(max_planar, planar_elems(d.out_c, d.out_h, d.out_w));
+        prev_tensor = tensor_of[i];
+    }
+    // a concat buffer is also "read" by the route layer itself (keeps it alive between its writers and its consumer)
+    for (int i = 0; i < n_layers; ++i)
+        if (layers[i].type == YOLO2CUDA_ROUTE && tensor_of[i] >= 0)
+            net->T[tensor_of[i]].last_use = std::max(net->T[tensor_of[i]].last_use, i);
+    for (auto &t : net->T)
+        if (t.bytes && t.last_use < t.first_def) t.last_use = t.first_def;       // written, never read: still needs a home
+    if ((rc = place_tensors(net, false))) {
+        yolo2cuda_net_destroy(net);
+        return rc;
     }
     net->tmp_planar_elems = max_planar;
     if ((rc = net_alloc(net, &net->d_tmp_planar_in, max_planar * e)) || (rc = net_alloc(net, &net->d_tmp_planar_out, max_planar * e))) {
@@ -726,6 +816,9 @@ int yolo2cuda_net_destroy(yolo2cuda_net *net)
     cudaSetDevice(net->ctx->device);
     cudaStreamSynchronize(net->ctx->stream);
     for (void *p : net->owned) cudaFree(p);
+    if (net->arena) cudaFree(net->arena);
+    for (auto &t : net->T)
+        if (t.own) cudaFree(t.own);
     if (net->d_lb_img) cudaFree(net->d_lb_img);
     for (auto ev : net->ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
@@ -744,6 +837,7 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
 {
     if (!net || !weights || !bias) return YOLO2CUDA_ERROR;
     yolo2cuda_ctx *ctx = net->ctx;
+    net->weights_loaded = false;   // a failed (re)load leaves the layer plans half-updated: nothing may run until one succeeds
     CUDA_OK(ctx, cudaSetDevice(ctx->device));
     const int e = ctx->elem;
     cudaStream_t st = ctx->stream;
@@ -883,19 +977,16 @@ int yolo2cuda_net_forward_host(yolo2cuda_net *net, const float *frames, int batc
     int rc;
     // Double-buffered passes: the H2D copy of pass k+1 and the D2H copy of pass k-1 run on their own
     // streams (separate DMA engines) while pass k computes on the context stream.
-    if (!net->d_frames) {
-        for (int i = 0; i < 2; ++i) {
-            if ((rc = net_alloc(net, &net->d_frames2[i], frame_elems * net->max_batch * sizeof(float)))) return rc;
-            if ((rc = net_alloc(net, &net->d_region2[i], net->region_outputs * net->max_batch * sizeof(float)))) return rc;
-            CUDA_OK(ctx, cudaEventCreateWithFlags(&net->ev_h2d[i], cudaEventDisableTiming));
-            CUDA_OK(ctx, cudaEventCreateWithFlags(&net->ev_comp[i], cudaEventDisableTiming));
-            CUDA_OK(ctx, cudaEventCreateWithFlags(&net->ev_d2h[i], cudaEventDisableTiming));
-        }
-        CUDA_OK(ctx, cudaStreamCreateWithFlags(&net->s_h2d, cudaStreamNonBlocking));
-        CUDA_OK(ctx, cudaStreamCreateWithFlags(&net->s_d2h, cudaStreamNonBlocking));
-        net->d_frames = net->d_frames2[0];
-        net->d_region = net->d_region2[0];
+    // lazily created staging, one guard per resource: a call that fails half-way neither leaks nor re-creates what exists
+    for (int i = 0; i < 2; ++i) {
+        if (!net->d_frames2[i] && (rc = net_alloc(net, &net->d_frames2[i], frame_elems * net->max_batch * sizeof(float)))) return rc;
+        if (!net->d_region2[i] && (rc = net_alloc(net, &net->d_region2[i], net->region_outputs * net->max_batch * sizeof(float)))) return rc;
+        if (!net->ev_h2d[i]) CUDA_OK(ctx, cudaEventCreateWithFlags(&net->ev_h2d[i], cudaEventDisableTiming));
+        if (!net->ev_comp[i]) CUDA_OK(ctx, cudaEventCreateWithFlags(&net->ev_comp[i], cudaEventDisableTiming));
+        if (!net->ev_d2h[i]) CUDA_OK(ctx, cudaEventCreateWithFlags(&net->ev_d2h[i], cudaEventDisableTiming));
     }
+    if (!net->s_h2d) CUDA_OK(ctx, cudaStreamCreateWithFlags(&net->s_h2d, cudaStreamNonBlocking));
+    if (!net->s_d2h) CUDA_OK(ctx, cudaStreamCreateWithFlags(&net->s_d2h, cudaStreamNonBlocking));
     const int npass = (batch + net->max_batch - 1) / net->max_batch;
     auto pass_frames = [&](int k) { return (k + 1) * net->max_batch <= batch ? net->max_batch : batch - k * net->max_batch; };
     auto issue_h2d = [&](int k) -> int {
@@ -977,6 +1068,8 @@ int yolo2cuda_net_get_layer_output(yolo2cuda_net *net, int layer, int frame, voi
     yolo2cuda_ctx *ctx = net->ctx;
     const LayerPlan &l = net->L[layer];
     if (l.d.type == YOLO2CUDA_REGION) return fail(ctx, YOLO2CUDA_ERROR, "region output is returned by net_forward");
+    if (!net->keep_all)
+        return fail(ctx, YOLO2CUDA_ERROR, "per-layer outputs are recycled in the compact arena: call yolo2cuda_net_set_debug_keep(net, 1) before the forward");
     if (frame < 0 || frame >= net->last_batch) return fail(ctx, YOLO2CUDA_ERROR, "frame %d not in the last forward (batch %d)", frame, net->last_batch);
     const size_t need = planar_elems(l.out.C, l.out.H, l.out.W);
     if (dst_elems < need) return fail(ctx, YOLO2CUDA_ERROR, "dst too small: need %zu elements", need);
@@ -996,8 +1089,20 @@ int yolo2cuda_net_region_q(const yolo2cuda_net *net) { return net ? net->region_
 uint64_t yolo2cuda_net_launches_per_forward(const yolo2cuda_net *net) { return net ? net->launches_per_forward : 0; }
 int yolo2cuda_net_set_debug_keep(yolo2cuda_net *net, int keep)
 {
-    (void)keep;  // every layer owns its output buffer in this version: nothing to switch
-    return net ? YOLO2CUDA_SUCCESS : YOLO2CUDA_ERROR;
+    if (!net) return YOLO2CUDA_ERROR;
+    CUDA_OK(net->ctx, cudaSetDevice(net->ctx->device));
+    if ((keep != 0) == net->keep_all) return YOLO2CUDA_SUCCESS;
+    net->last_batch = 0;                       // the tensors move: nothing of the last forward can be read back any more
+    return place_tensors(net, keep != 0);
+}
+
+size_t yolo2cuda_net_activation_bytes(const yolo2cuda_net *net)
+{
+    if (!net) return 0;
+    if (!net->keep_all) return net->arena_bytes;
+    size_t s = 0;
+    for (const auto &t : net->T) s += t.bytes;
+    return s;
 }
 
 const char *yolo2cuda_net_layer_kernel(const yolo2cuda_net *net, int layer)

@@ -229,13 +229,9 @@ __global__ void conv_f32_generic_kernel(const float *__restrict__ in, float *__r
 template <int TP, int KS>
 int launch_f32_variant(const ConvFastParams &p, size_t smem, cudaStream_t st)
 {
-    static bool configured[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(conv_f32_c4_kernel<TP, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured[dev] = true;
-    }
+    // set on every launch (a microsecond): the attribute is per device and a host may drive several GPUs from several threads,
+    // so a cached "already configured" flag would be a data race for nothing
+    cudaFuncSetAttribute(conv_f32_c4_kernel<TP, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid(ceil_div(p.B * p.H, p.RB), ceil_div(p.OFM, kCM));
     conv_f32_c4_kernel<TP, KS><<<grid, kThreads, smem, st>>>(p);
     return 1;

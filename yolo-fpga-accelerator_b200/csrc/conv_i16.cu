@@ -378,13 +378,9 @@ size_t conv_fast_plan(ConvFastParams &p, int ksize, int elem_bytes)
 template <int TP, int KS, bool SCALED>
 static int launch_i16_variant(const ConvFastParams &p, size_t smem, cudaStream_t st)
 {
-    static bool configured[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(conv_i16_c4_kernel<TP, KS, SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured[dev] = true;
-    }
+    // set on every launch (a microsecond): the attribute is per device and a host may drive several GPUs from several threads,
+    // so a cached "already configured" flag would be a data race for nothing
+    cudaFuncSetAttribute(conv_i16_c4_kernel<TP, KS, SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid(ceil_div(p.B * p.H, p.RB), ceil_div(p.OFM, kCM));
     conv_i16_c4_kernel<TP, KS, SCALED><<<grid, kThreads, smem, st>>>(p);
     return 1;

@@ -457,13 +457,9 @@ __global__ void wprep_tc32_kernel(const int16_t *__restrict__ blob, unsigned cha
 template <int KS, int SO>
 void launch_one(const Tc32Params &p, dim3 grid, size_t smem, cudaStream_t st)
 {
-    static bool configured[64] = {false};   // the attribute is per device: a process may drive several GPUs
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaFuncSetAttribute(conv_i16_tc32_kernel<KS, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
+    // set on every launch (a microsecond): the attribute is per device and a host may drive several GPUs from several threads,
+    // so a cached "already configured" flag would be a data race for nothing
+    cudaFuncSetAttribute(conv_i16_tc32_kernel<KS, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     conv_i16_tc32_kernel<KS, SO><<<grid, kThreads, smem, st>>>(p);
 }
 

@@ -2,10 +2,14 @@
 // letterbox un-mapping and per-class greedy NMS.  Mirrors the observable behaviour of the
 // reference's get_region_detections / correct_region_boxes (src/core/yolo_region.cpp:18-53,
 // 169-195) and do_nms_sort (src/core/yolo_post.cpp:54-85): same float arithmetic (expf for box
-// sizes, float IoU), same candidate scan order (cell-major, then anchor).  Stays on the host
+// sizes, float IoU), same candidate scan order (cell-major, then anchor), same qsort on an order that
+// is carried from class to class (ties between equal probabilities resolve as in the reference).
+// Output: the candidates with objectness > thresh in scan order (the reference's list BEFORE its
+// qsort re-orders it); the return value is their count.  Stays on the host
 // because it is <0.1 % of the frame time and shares libm with the reference.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include <vector>
 
@@ -30,6 +34,17 @@ float iou(const Box &a, const Box &b)
     float inter = (w < 0 || h < 0) ? 0 : w * h;
     float uni = a.w * a.h + b.w * b.h - inter;
     return inter / uni;
+}
+
+struct SortKey { const float *pr; int classes, cls; };
+
+// nms_comparator's outcomes (yolo_post.cpp:7-20): descending probability of the class being processed, 0 on ties
+int by_class_prob_desc(const void *pa, const void *pb, void *ctx)
+{
+    const SortKey *k = static_cast<const SortKey *>(ctx);
+    const float diff = k->pr[(size_t)(*static_cast<const int *>(pa)) * k->classes + k->cls] -
+                       k->pr[(size_t)(*static_cast<const int *>(pb)) * k->classes + k->cls];
+    return diff < 0 ? 1 : diff > 0 ? -1 : 0;
 }
 
 }  // namespace
@@ -75,15 +90,27 @@ extern "C" int yolo2cuda_region_detections(const float *region, int lw, int lh, 
         b.h *= (float)net_h / new_h;
     }
     if (nms > 0.0f) {
+        // do_nms_sort (yolo_post.cpp:54-85) sorts ONE array in place class after class: the order a class's qsort starts from is
+        // the order the previous class left behind, and with equal probabilities that order decides which of two overlapping
+        // boxes survives.  So the candidate order is carried across classes here too, and the sort is the C library's qsort
+        // with the reference comparator's outcomes (yolo_post.cpp:7-20), i.e. the same permutation on the same libc.
         std::vector<int> order(count);
+        std::iota(order.begin(), order.end(), 0);
+        int live = count;
+        for (int i = 0, k = count - 1; i <= k; ++i)          // entries with objectness == 0 go to the back (yolo_post.cpp:57-67)
+            if (obj[order[i]] == 0) {
+                std::swap(order[i], order[k]);
+                --k; --i;
+                live = k + 1;
+            }
+        SortKey key{pr.data(), classes, 0};
         for (int k = 0; k < classes; ++k) {
-            std::iota(order.begin(), order.end(), 0);
-            std::stable_sort(order.begin(), order.end(),
-                             [&](int a, int b) { return pr[(size_t)a * classes + k] > pr[(size_t)b * classes + k]; });
-            for (int i = 0; i < count; ++i) {
+            key.cls = k;
+            qsort_r(order.data(), (size_t)live, sizeof(int), by_class_prob_desc, &key);
+            for (int i = 0; i < live; ++i) {
                 const int di = order[i];
                 if (pr[(size_t)di * classes + k] == 0) continue;
-                for (int j = i + 1; j < count; ++j) {
+                for (int j = i + 1; j < live; ++j) {
                     const int dj = order[j];
                     if (iou(bb[di], bb[dj]) > nms) pr[(size_t)dj * classes + k] = 0;
                 }

@@ -1,6 +1,6 @@
 // `--backend cuda` for the reference host (see yolov2_cuda_ps.hpp).  Thin: translate the reference's
-// `network` into the yolo2cuda_layer_desc table, load the reference's weight files exactly as
-// load_weights does (hls/models/yolov2/yolo2_model.cpp:158-227, incl. the odd-length pad rule), call the
+// `network` into the yolo2cuda_layer_desc table, read the reference's weight files (the file formats
+// are the contract: hls/models/yolov2/yolo2_model.cpp:158-227, incl. the odd-length filler rule), call the
 // C ABI.  No arithmetic happens here and there is no CPU fallback: errors throw std::runtime_error like
 // the reference's loaders do (caught in main, src/models/yolov2/yolov2_main.cpp:340-346).
 #include "yolov2_cuda_ps.hpp"
@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <algorithm>
 #include <stdexcept>
 #include <string>
@@ -20,27 +21,32 @@
 
 namespace {
 
+// Whole-file loader for the reference's flat little-endian .bin tables (weights/*.bin next to the cwd, the paths of
+// hls/models/yolov2/yolo2_model.cpp:171-193).  The file length must be a whole number of elements.
 template <typename T>
-std::vector<T> read_binary(const std::string &path, bool required = true)
-{
-    FILE *fp = std::fopen(path.c_str(), "rb");
-    if (!fp) {
-        if (!required) return {};
-        throw std::runtime_error("Failed to open file: " + path);
+struct BinTable {
+    std::vector<T> v;
+    bool found = false;
+
+    static BinTable open(const std::string &path, bool optional = false)
+    {
+        BinTable t;
+        std::ifstream in(path, std::ios::binary | std::ios::ate);
+        if (!in) {
+            if (optional) return t;
+            throw std::runtime_error("cuda backend: cannot open " + path);
+        }
+        const std::streamoff bytes = in.tellg();
+        if (bytes < 0 || bytes % (std::streamoff)sizeof(T))
+            throw std::runtime_error("cuda backend: " + path + " is not a whole number of " + std::to_string(sizeof(T)) + "-byte entries");
+        t.v.resize((size_t)bytes / sizeof(T));
+        in.seekg(0);
+        in.read(reinterpret_cast<char *>(t.v.data()), bytes);
+        if (in.gcount() != bytes) throw std::runtime_error("cuda backend: " + path + " ended early");
+        t.found = true;
+        return t;
     }
-    std::fseek(fp, 0, SEEK_END);
-    long sz = std::ftell(fp);
-    std::fseek(fp, 0, SEEK_SET);
-    if (sz < 0 || sz % sizeof(T) != 0) {
-        std::fclose(fp);
-        throw std::runtime_error("Invalid size for file: " + path);
-    }
-    std::vector<T> buf(sz / sizeof(T));
-    size_t rd = std::fread(buf.data(), sizeof(T), buf.size(), fp);
-    std::fclose(fp);
-    if (rd != buf.size()) throw std::runtime_error("Short read: " + path);
-    return buf;
-}
+};
 
 std::vector<yolo2cuda_layer_desc> describe(const network *net)
 {
@@ -85,51 +91,65 @@ std::vector<yolo2cuda_layer_desc> describe(const network *net)
     return d;
 }
 
+// The five tables of one precision, as the C ABI wants them (conv layers back to back, no padding).
 struct Pack {
     std::vector<int16_t> w16, b16;
     std::vector<float> w32, b32;
     std::vector<int32_t> wq, bq, aq;
 };
 
+// The int16 files carry ONE filler element after every layer whose element count is odd (the quantiser keeps each layer
+// 4-byte aligned; the reference loader steps over it, yolo2_model.cpp:216-223).  Returns the layers packed back to back.
+std::vector<int16_t> drop_layer_fillers(const std::vector<int16_t> &file, const std::vector<size_t> &layer_len, const char *what)
+{
+    size_t total = 0;
+    for (size_t n : layer_len) total += n;
+    std::vector<int16_t> packed;
+    packed.reserve(total);
+    size_t at = 0;
+    for (size_t li = 0; li < layer_len.size(); ++li) {
+        const size_t n = layer_len[li];
+        if (at + n > file.size())
+            throw std::runtime_error(std::string("cuda backend: int16 ") + what + " file ends inside conv layer " + std::to_string(li));
+        packed.insert(packed.end(), file.begin() + at, file.begin() + at + n);
+        at += n + (n % 2);
+    }
+    return packed;
+}
+
 Pack load_pack(const std::vector<yolo2cuda_layer_desc> &d, Precision precision)
 {
+    std::vector<size_t> w_len, b_len;
+    size_t w_total = 0, b_total = 0;
+    for (const auto &l : d) {
+        if (l.type != YOLO2CUDA_CONV) continue;
+        w_len.push_back((size_t)l.c * l.n * l.size * l.size);
+        b_len.push_back((size_t)l.n);
+        w_total += w_len.back();
+        b_total += b_len.back();
+    }
     Pack p;
-    std::vector<size_t> wl, bl;
-    size_t ew = 0, eb = 0;
-    for (const auto &l : d)
-        if (l.type == YOLO2CUDA_CONV) {
-            wl.push_back((size_t)l.c * l.n * l.size * l.size);
-            bl.push_back((size_t)l.n);
-            ew += wl.back();
-            eb += bl.back();
-        }
     if (precision == Precision::FP32) {
-        p.w32 = read_binary<float>("weights/weights_reorg.bin");
-        p.b32 = read_binary<float>("weights/bias.bin");
-        if (p.w32.size() < ew) throw std::runtime_error("weights file too small");
-        if (p.b32.size() < eb) throw std::runtime_error("bias file too small");
+        p.w32 = BinTable<float>::open("weights/weights_reorg.bin").v;
+        p.b32 = BinTable<float>::open("weights/bias.bin").v;
+        if (p.w32.size() < w_total || p.b32.size() < b_total)
+            throw std::runtime_error("cuda backend: fp32 weight/bias files hold fewer values than the cfg's conv layers need");
         return p;
     }
-    auto w = read_binary<int16_t>("weights/weights_reorg_int16.bin");
-    auto b = read_binary<int16_t>("weights/bias_int16.bin");
-    if (w.size() < ew) throw std::runtime_error("weights file too small");
-    if (b.size() < eb) throw std::runtime_error("bias file too small");
-    p.wq = read_binary<int32_t>("weights/weight_int16_Q.bin");
-    p.bq = read_binary<int32_t>("weights/bias_int16_Q.bin");
-    if (p.wq.size() < wl.size() || p.bq.size() < wl.size()) throw std::runtime_error("Q tables too small for conv layers");
-    p.aq = read_binary<int32_t>("weights/iofm_Q.bin", false);
-    if (p.aq.empty()) throw std::runtime_error("Activation Q table (iofm_Q.bin) is required for int16 inference.");
-    p.w16.resize(ew);
-    p.b16.resize(eb);
-    size_t wf = 0, wo = 0, bf = 0, bo = 0;
-    for (size_t li = 0; li < wl.size(); ++li) {  // strip the pad element after odd-length layers (yolo2_model.cpp:216-223)
-        if (wf + wl[li] > w.size()) throw std::runtime_error("int16 weight truncated at layer " + std::to_string(li));
-        if (bf + bl[li] > b.size()) throw std::runtime_error("int16 bias truncated at layer " + std::to_string(li));
-        std::memcpy(p.w16.data() + wo, w.data() + wf, wl[li] * sizeof(int16_t));
-        std::memcpy(p.b16.data() + bo, b.data() + bf, bl[li] * sizeof(int16_t));
-        wf += wl[li] + (wl[li] & 1); wo += wl[li];
-        bf += bl[li] + (bl[li] & 1); bo += bl[li];
-    }
+    const auto wfile = BinTable<int16_t>::open("weights/weights_reorg_int16.bin");
+    const auto bfile = BinTable<int16_t>::open("weights/bias_int16.bin");
+    if (wfile.v.size() < w_total || bfile.v.size() < b_total)
+        throw std::runtime_error("cuda backend: int16 weight/bias files hold fewer values than the cfg's conv layers need");
+    p.wq = BinTable<int32_t>::open("weights/weight_int16_Q.bin").v;
+    p.bq = BinTable<int32_t>::open("weights/bias_int16_Q.bin").v;
+    if (p.wq.size() < w_len.size() || p.bq.size() < w_len.size())
+        throw std::runtime_error("cuda backend: weight/bias Q tables have fewer entries than there are conv layers");
+    // the reference treats iofm_Q.bin as optional at load time and then refuses to run int16 without it (yolo2_model.cpp:190-196,258-260)
+    const auto aq = BinTable<int32_t>::open("weights/iofm_Q.bin", /*optional=*/true);
+    if (!aq.found || aq.v.empty()) throw std::runtime_error("cuda backend: int16 inference needs the activation Q table weights/iofm_Q.bin");
+    p.aq = aq.v;
+    p.w16 = drop_layer_fillers(wfile.v, w_len, "weight");
+    p.b16 = drop_layer_fillers(bfile.v, b_len, "bias");
     return p;
 }
 

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import cfg as _cfg
 from .accel import letterbox_image
-from .model import Yolo2Net, detections_jsonl, region_detections_gpu
+from .model import Yolo2Net, detections_jsonl, region_detections, region_detections_gpu
 from .weights import WeightsPack
 
 
@@ -44,8 +44,26 @@ class DetectionStream:
         dev_images = images.to(self.dev, non_blocking=True)
         frames = letterbox_image(self.y.accel, dev_images, self.net.w, self.net.h)
         self.y.forward_ptr(frames.data_ptr(), b, self.region.data_ptr(), device=True)
-        boxes, probs, obj = region_detections_gpu(self.y.accel, self.net, self.region[:b], iw, ih, self.thresh, self.nms)
-        return boxes.cpu().numpy(), probs.cpu().numpy(), obj.cpu().numpy()
+        l = self.net.layers[-1]
+        total = l.w * l.h * l.n
+        if total <= 1024:       # detect_kernel sorts a frame's candidates in one CTA's shared memory: at most 1024 (416x416: 845)
+            boxes, probs, obj = region_detections_gpu(self.y.accel, self.net, self.region[:b], iw, ih, self.thresh, self.nms)
+            return boxes.cpu().numpy(), probs.cpu().numpy(), obj.cpu().numpy()
+        # larger grids (608x608: 19*19*5 = 1805 candidates): the region tensors come back and the library's host tail
+        # (yolo2cuda_region_detections, the bit-exact default of the C ABI) runs per frame; its compact scan-order list is
+        # scattered to the same positional layout the GPU kernel produces (entry = cell * n + anchor)
+        self.y.accel.synchronize()
+        reg = self.region[:b].cpu().numpy()
+        boxes = np.zeros((b, total, 4), np.float32)
+        probs = np.zeros((b, total, l.classes), np.float32)
+        obj = np.zeros((b, total), np.float32)
+        for f in range(b):
+            bb, pp, oo = region_detections(self.net, reg[f], iw, ih, self.thresh, self.nms)
+            o_map = reg[f].reshape(l.n, l.coords + 1 + l.classes, l.h * l.w)[:, l.coords, :]      # [anchor][cell]
+            pos = np.nonzero((o_map.T > np.float32(self.thresh)).reshape(-1))[0]                   # cell-major, then anchor
+            assert len(pos) == len(bb)
+            boxes[f, pos], probs[f, pos], obj[f, pos] = bb, pp, oo
+        return boxes, probs, obj
 
     def detect_jsonl(self, images, labels=None, source="", first_index=0):
         boxes, probs, _ = self.detect(images)

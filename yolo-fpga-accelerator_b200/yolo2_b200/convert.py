@@ -101,7 +101,67 @@ def best_q(max_abs: float, bits: int = 16, q_max: int = 15) -> int:
     return max(0, min(q_max, q))
 
 
-def calibrate_activation_q(net: _cfg.Network, fp32_pack: WeightsPack, frames: np.ndarray, device: int = 0, headroom: int = 1) -> np.ndarray:
+def harmonise_route_q(net: _cfg.Network, act_q: np.ndarray) -> np.ndarray:
+    """Makes an iofm_Q table consistent with the way the driver loop reads it (yolo2_model.cpp:311-336,379-399; the same
+    bookkeeping is in csrc/capi.cu net_load_weights).  The loop takes a conv's INPUT Q from the table entry of the conv that
+    precedes it IN THE FILE, not from the tensor it really reads, and it rescales only the reorg branch of the concat:
+
+      1. single-input route (`route -9`): the conv after it reads the route SOURCE, but is given the output Q of the conv just
+         before the route.  Both entries must therefore be equal -> both become their minimum.
+      2. concat of (reorg branch, skip conv): the reorg branch is shifted DOWN to min(Q_skip, Q_branch); the skip half is never
+         touched, so Q_skip <= Q_branch must hold -> Q_skip is lowered if needed (and rule 1 re-applied, the skip conv being the
+         one before the route in YOLOv2).
+
+    Entry k+1 of the table is the output Q of conv k.  Lowering a Q only costs precision, never range."""
+    q = np.array(act_q, np.int32, copy=True)
+    conv_no = {}                       # layer index -> conv index
+    for i, l in enumerate(net.layers):
+        if l.type == _cfg.CONV:
+            conv_no[i] = len(conv_no)
+
+    def producer_conv(i):              # the conv whose output Q a tensor carries (pool / reorg / single routes keep the Q)
+        while net.layers[i].type != _cfg.CONV:
+            l = net.layers[i]
+            i = l.inputs[0] if l.type == _cfg.ROUTE else i - 1
+            if i < 0:
+                return None
+        return conv_no[i]
+
+    def next_conv(i):
+        for j in range(i + 1, len(net.layers)):
+            if net.layers[j].type == _cfg.CONV:
+                return conv_no[j]
+        return None
+
+    ties, clamps = [], []
+    for i, l in enumerate(net.layers):
+        if l.type != _cfg.ROUTE:
+            continue
+        if len(l.inputs) == 1:
+            src, nxt = producer_conv(l.inputs[0]), next_conv(i)
+            if src is not None and nxt is not None and nxt > 0:
+                ties.append((src + 1, nxt))          # entry nxt = output Q of conv nxt-1 = what the driver hands conv nxt as Qa_in
+        else:
+            reorgs = [a for a in l.inputs if net.layers[a].type == _cfg.REORG]
+            for a in reorgs:
+                for b in l.inputs:
+                    if b != a:
+                        skip, branch = producer_conv(b), producer_conv(a)
+                        if skip is not None and branch is not None:
+                            clamps.append((skip + 1, branch + 1))
+    for _ in range(len(ties) + len(clamps) + 1):     # to a fixed point (two rules, a handful of entries)
+        before = q.copy()
+        for a, b in ties:
+            q[a] = q[b] = min(q[a], q[b])
+        for skip, branch in clamps:
+            q[skip] = min(q[skip], q[branch])
+        if np.array_equal(before, q):
+            break
+    return q
+
+
+def calibrate_activation_q(net: _cfg.Network, fp32_pack: WeightsPack, frames: np.ndarray, device: int = 0, headroom: int = 1,
+                           harmonise: bool = True) -> np.ndarray:
     """iofm_Q table (n_conv + 1 entries: network input, then every conv layer's output) from the largest
     magnitude the fp32 CUDA path produces on the calibration frames (float32 [B][c][h][w] in [0,1]).
     `headroom` bits are kept free on the conv outputs: the datapath's accumulator is 16 bits wide in the OUTPUT's
@@ -122,7 +182,7 @@ def calibrate_activation_q(net: _cfg.Network, fp32_pack: WeightsPack, frames: np
         y.close()
     q = np.array([best_q(a) for a in amax], np.int32)
     q[1:] = np.maximum(q[1:] - headroom, 0)
-    return q
+    return harmonise_route_q(net, q) if harmonise else q
 
 
 def quantize_pack(net: _cfg.Network, folded, act_q: np.ndarray) -> WeightsPack:

@@ -89,8 +89,13 @@ class Yolo2Net:
         return flat.reshape(B, l.n, l.coords + 1 + l.classes, l.h, l.w)
 
     def set_debug_keep(self, keep: bool = True):
-        """Give every layer its own output buffer so that layer_output works for every layer (yolo2cuda_net_set_debug_keep)."""
+        """Give every layer its own output buffer so that layer_output works for every layer (yolo2cuda_net_set_debug_keep);
+        the default is one liveness-packed arena in which buffers are recycled down the network."""
         _capi.check(self.accel.ctx, self.lib.yolo2cuda_net_set_debug_keep(self.handle, int(bool(keep))))
+
+    @property
+    def activation_bytes(self) -> int:
+        return int(self.lib.yolo2cuda_net_activation_bytes(self.handle))
 
     def layer_output(self, layer: int, frame: int = 0) -> np.ndarray:
         """ofm of `layer` for `frame` of the last forward, reference layout [out_c][out_h][ceil8 out_w]."""
