@@ -71,6 +71,10 @@ const char *yolo2cuda_last_error(const yolo2cuda_ctx *ctx);
 uint64_t yolo2cuda_launch_count(const yolo2cuda_ctx *ctx);
 /* Name of the kernel variant chosen by the last conv launch (diagnostics / tests). */
 const char *yolo2cuda_last_kernel(const yolo2cuda_ctx *ctx);
+/* Diagnostics of the tcgen05 conv kernel (csrc/conv_i16_tc2.cu): how many (warp, tile) units went through its no-saturation fast
+ * path and how many through the exact step, since context creation or the last reset.  Both paths produce the reference's
+ * bits; the environment variable YOLO2CUDA_TC_EXACT=1 (read at yolo2cuda_create) disables the fast path.  Synchronises. */
+int yolo2cuda_tc_path_counts(yolo2cuda_ctx *ctx, uint64_t *fast_tiles, uint64_t *exact_tiles, int reset);
 
 /* ---- one accelerator call: replaces YOLO2_FPGA --------------------------------------------
  * Argument order, meaning and limits are those of yolo2_accel.hpp:10-17 / yolo2_accel.cpp:75-87.

@@ -51,5 +51,7 @@ for i, (l, t) in enumerate(zip(net.layers, ms)):
         t = float(t); by = (l.c * l.h * l.w * eb + l.c * l.h * l.w * 4) * batch
         r["GBps"] = by / (t * 1e-3) / 1e9
         r["frac_of_hbm_peak"] = r["GBps"] / peaks["hbm_gbs"]
+    r["kernel"] = y.layer_kernel(i)
     rows.append(r)
-print(json.dumps({"batch": batch, "precision": precision, "tn": tn, "size": size, "classes": classes, "total_ms": tot, "fps": batch / (tot * 1e-3), "layers": rows}, indent=1))
+fast_tiles, exact_tiles = acc.tc_path_counts() if precision == "int16" else (0, 0)
+print(json.dumps({"tc_fast_tiles": fast_tiles, "tc_exact_tiles": exact_tiles, "activation_bytes": y.activation_bytes, "batch": batch, "precision": precision, "tn": tn, "size": size, "classes": classes, "total_ms": tot, "fps": batch / (tot * 1e-3), "layers": rows}, indent=1))

@@ -373,6 +373,86 @@ def test_tensor_core_v2_every_shift(so, monkeypatch, oracle):
         acc.close()
 
 
+@pytest.mark.parametrize("so", list(range(8, 17)))
+def test_tensor_core_fast_path_every_shift(so, monkeypatch, oracle):
+    """moderate operands: most (warp, tile) units pass the no-saturation test and take the two-instruction step (HH from the dense
+    column, 65536 HH a multiple of 2^so), some fail it and take the exact step in the same launch; every shift instantiation"""
+    from yolo2_b200.accel import Accelerator
+    monkeypatch.setenv("YOLO2CUDA_TC", "2")
+    acc = Accelerator(0, "int16")
+    try:
+        q = (so - 2, 10, 8, 9)
+        # the single-call entry knows nothing about the caller's tensor, so the bound assumes |x| <= 32768: Dsum = sum|w| * 2^(15-so).
+        # Small weights (sum over 28 of them < 2^so / 4) keep it below the int16 range for every shift; the activations stay large.
+        amp = max(2, (1 << so) // 512)
+        for (c, n, k, w, h) in ((96, 130, 3, 13, 13), (200, 128, 1, 26, 5)):
+            a, x, wr, b, _ = make_conv_case(so * 10 + c, c, n, k, 1, w, h, 1, amp=amp, xamp=12000)
+            want = oracle_conv(oracle, a, x, wr, b, q)
+            acc.tc_path_counts(reset=True)
+            got = accel_call(acc, a, x, wr, b, q)
+            fast, exact = acc.tc_path_counts()
+            assert acc.last_kernel.startswith("conv_i16_tc2<")
+            assert np.array_equal(valid(got, w), valid(want, w))
+            assert fast > 0, (so, fast, exact)
+    finally:
+        acc.close()
+
+
+@pytest.mark.parametrize("xamp,expect_mixed", [(300, False), (9000, True), (20000, True)])
+def test_tensor_core_fast_and_exact_paths_mix(xamp, expect_mixed, monkeypatch, oracle):
+    """deep chains (2304 steps) whose accumulators wander towards the int16 limits: the per-K-block range test sends the risky
+    tiles to the exact step and the rest to the fast one; the result is the reference's bits whatever the mix.  With
+    YOLO2CUDA_TC_EXACT=1 the fast path is off and the bits are the same."""
+    from yolo2_b200.accel import Accelerator
+    a, x, wr, b, _ = make_conv_case(4242 + xamp, 1024, 128, 3, 1, 13, 13, 1, amp=600, xamp=xamp)
+    q = (14, 10, 10, 10)
+    want = oracle_conv(oracle, a, x, wr, b, q)
+    for force_exact in ("0", "1"):
+        monkeypatch.setenv("YOLO2CUDA_TC", "2")
+        monkeypatch.setenv("YOLO2CUDA_TC_EXACT", force_exact)
+        acc = Accelerator(0, "int16")
+        try:
+            got = accel_call(acc, a, x, wr, b, q)
+            fast, exact = acc.tc_path_counts()
+            assert np.array_equal(valid(got, 13), valid(want, 13)), (xamp, force_exact)
+            if force_exact == "1":
+                assert fast == 0 and exact > 0
+            else:
+                assert fast > 0 and (exact > 0) == expect_mixed, (xamp, fast, exact)
+        finally:
+            acc.close()
+    if xamp == 20000:
+        assert (np.abs(valid(want, 13).astype(int)) >= 32767).any()        # the case really saturates somewhere
+
+
+def test_tensor_core_net_fast_path_statistics(monkeypatch, oracle):
+    """inside the network executor the bound uses the producing layer's tracked maximum |activation|: on the default table nearly
+    every tile of a thin net takes the fast path, on the saturating table the exact path runs; both bit-exact (checked against the
+    oracle in test_tensor_core_net_bit_exact) and identical to a run with the fast path disabled"""
+    from yolo2_b200.accel import Accelerator
+    regions = {}
+    for table in ("default", "saturate"):
+        for force_exact in ("0", "1"):
+            monkeypatch.setenv("YOLO2CUDA_TC", "2")
+            monkeypatch.setenv("YOLO2CUDA_TC_MIN_OFM", "8")
+            monkeypatch.setenv("YOLO2CUDA_TC_EXACT", force_exact)
+            net, pack = _net_case(416, 416, 3, 8, table, seed=11)
+            frames = yw.synth_frames(net, 3, seed=2000)
+            y = Yolo2Net(net, pack, max_batch=3)
+            try:
+                regions[(table, force_exact)] = y.forward(frames).copy()
+                fast, exact = y.accel.tc_path_counts()
+            finally:
+                y.close()
+            if force_exact == "1":
+                assert fast == 0 and exact > 0
+            elif table == "default":
+                assert fast > 20 * max(exact, 1), (fast, exact)
+            else:
+                assert exact > 0
+        assert np.array_equal(regions[(table, "0")].view(np.uint32), regions[(table, "1")].view(np.uint32))
+
+
 @pytest.mark.parametrize("table", ["stress", "saturate", "default"])
 def test_tensor_core_net_bit_exact(table, monkeypatch, oracle):
     monkeypatch.setenv("YOLO2CUDA_TC", "2")

@@ -30,6 +30,8 @@ struct yolo2cuda_ctx {
     int use_tc = -1;  // YOLO2CUDA_TC: unset = auto (the tcgen05 kernel csrc/conv_i16_tc2.cu on the layers where it measured faster),
                       // 0 = CUDA-core kernels only, anything else = the tcgen05 kernel wherever the shape is eligible (tests / profiling)
     int tc_min_ofm = 96;
+    int tc_force_exact = 0;          // YOLO2CUDA_TC_EXACT=1: the tcgen05 kernel never takes its no-saturation fast path (tests)
+    unsigned long long *d_tc_stats = nullptr;   // device [2]: warp-tiles of the tcgen05 kernel through the fast / the exact path
     // growable device scratch for the per-layer entry points
     struct Scratch { void *p = nullptr; size_t bytes = 0; } s_in, s_out, s_w, s_b, s_c4in, s_c4out, s_wprep;
 };
@@ -167,6 +169,7 @@ int run_conv_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, cons
         p.in = ctx->s_c4in.p; p.out = ctx->s_c4out.p; p.w = ctx->s_wprep.p; p.bias = Beta;
         p.in_frame_stride = 0; p.out_frame_stride = 0;
         p.so = so; p.sb = sb; p.leaky = IsNL;
+        p.tc_stats = ctx->d_tc_stats; p.tc_force_exact = ctx->tc_force_exact;     // (xmax_in = NULL: the caller's tensor is unknown, 32768 is assumed)
         if (launch_conv_i16_tc2(p, K, st, &ctx->last_kernel) < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "tc conv not eligible");
         launch_c4_to_planar(ctx->s_c4out.p, Output, 1, OFM, Oh, Ow, 0, 0, ctx->elem, st);
         ctx->launches += 4;
@@ -221,6 +224,14 @@ int yolo2cuda_create(yolo2cuda_ctx **out, int device, int precision)
     const char *tc = getenv("YOLO2CUDA_TC");
     ctx->use_tc = (tc && tc[0]) ? (tc[0] == '0' ? 0 : 2) : -1;
     if (const char *mo = getenv("YOLO2CUDA_TC_MIN_OFM")) ctx->tc_min_ofm = atoi(mo);
+    const char *ex = getenv("YOLO2CUDA_TC_EXACT");
+    ctx->tc_force_exact = (ex && ex[0] && ex[0] != '0') ? 1 : 0;
+    if (cudaMalloc(&ctx->d_tc_stats, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_tc_stats, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return YOLO2CUDA_MEMORY_ERROR;
+    }
     *out = ctx;
     return YOLO2CUDA_SUCCESS;
 }
@@ -233,8 +244,22 @@ int yolo2cuda_destroy(yolo2cuda_ctx *ctx)
     yolo2cuda_ctx::Scratch *all[] = {&ctx->s_in, &ctx->s_out, &ctx->s_w, &ctx->s_b, &ctx->s_c4in, &ctx->s_c4out, &ctx->s_wprep};
     for (auto *s : all)
         if (s->p) cudaFree(s->p);
+    if (ctx->d_tc_stats) cudaFree(ctx->d_tc_stats);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+    return YOLO2CUDA_SUCCESS;
+}
+
+int yolo2cuda_tc_path_counts(yolo2cuda_ctx *ctx, uint64_t *fast_tiles, uint64_t *exact_tiles, int reset)
+{
+    if (!ctx) return YOLO2CUDA_ERROR;
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long h[2] = {0, 0};
+    CUDA_OK(ctx, cudaMemcpy(h, ctx->d_tc_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    if (fast_tiles) *fast_tiles = h[0];
+    if (exact_tiles) *exact_tiles = h[1];
+    if (reset) CUDA_OK(ctx, cudaMemset(ctx->d_tc_stats, 0, sizeof(h)));
     return YOLO2CUDA_SUCCESS;
 }
 
@@ -438,6 +463,12 @@ struct yolo2cuda_net {
     struct Tensor { size_t bytes = 0; int first_def = 1 << 30, last_use = -1; size_t offset = 0; void *own = nullptr; };
     std::vector<Tensor> T;
     std::vector<int> concat_of, concat_goff;   // per layer: the route whose concat buffer this layer writes into (-1), and its group offset
+    std::vector<int> tensor_in, tensor_out;    // per layer: tensor read / written (-1: none)
+    // largest-|activation| bookkeeping for the tcgen05 kernel's fast path: one device int per tensor CLASS (tensors joined by
+    // max-pool / reorg / concat share a slot: those operators never increase the largest magnitude)
+    int *d_xmax = nullptr;
+    std::vector<int> xslot;        // per tensor: slot index
+    std::vector<char> xknown;      // per slot: every writer of the class leaves its maximum behind
     void *arena = nullptr;         // compact mode: one allocation, tensors at liveness-packed offsets
     size_t arena_bytes = 0;
     bool keep_all = false;         // debug mode: every tensor owns its memory, so every layer's ofm survives the forward
@@ -587,6 +618,7 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
     const int e = ctx->elem;
     uint64_t launches = 0;
     const long long in_stride = (long long)c4_elems(net->in_c, net->in_h, net->in_w);
+    if (net->d_xmax) cudaMemsetAsync(net->d_xmax, 0, net->T.size() * sizeof(int), st);   // this pass's largest |activation| per tensor class
     launch_frames_to_c4(frames_dev, net->d_input_c4, B, net->in_c, net->in_h, net->in_w, in_stride,
                         net->input_q, e, st);
     ++launches;
@@ -749,6 +781,7 @@ int yolo2cuda_net_create(yolo2cuda_ctx *ctx, const yolo2cuda_layer_desc *layers,
     net->T[0].first_def = -1;
     size_t max_planar = planar_elems(net->in_c, net->in_h, net->in_w);
     std::vector<int> tensor_of(n_layers, -1);      // tensor a layer's OUTPUT view lives in
+    net->tensor_in.assign(n_layers, -1);
     int prev_tensor = 0;                           // tensor the next non-route layer reads
     for (int i = 0; i < n_layers; ++i) {
         const yolo2cuda_layer_desc &d = layers[i];
@@ -766,6 +799,7 @@ int yolo2cuda_net_create(yolo2cuda_ctx *ctx, const yolo2cuda_layer_desc *layers,
                 NET_FAIL("layer %d: input dims %dx%dx%d do not match the previous output %dx%dx%d", i, d.c, d.h, d.w,
                          layers[i - 1].out_c, layers[i - 1].out_h, layers[i - 1].out_w);
             touch_read(prev_tensor);
+            net->tensor_in[i] = prev_tensor;
             if (d.type == YOLO2CUDA_REGION) {
                 net->region_outputs = (size_t)d.c * d.h * d.w;
             } else {
@@ -784,6 +818,11 @@ int yolo2cuda_net_create(yolo2cuda_ctx *ctx, const yolo2cuda_layer_desc *layers,
             net->T[tensor_of[i]].last_use = std::max(net->T[tensor_of[i]].last_use, i);
     for (auto &t : net->T)
         if (t.bytes && t.last_use < t.first_def) t.last_use = t.first_def;       // written, never read: still needs a home
+    net->tensor_out = tensor_of;
+    if (e == 2 && (rc = net_alloc(net, (void **)&net->d_xmax, (1 + n_layers) * sizeof(int)))) {
+        yolo2cuda_net_destroy(net);
+        return rc;
+    }
     if ((rc = place_tensors(net, false))) {
         yolo2cuda_net_destroy(net);
         return rc;
@@ -918,11 +957,11 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                     l.cp = p;
                     // tensor-core path: wide layers only (a CTA covers 128 output channels)
                     l.tc = ctx->use_tc > 0 && e == 2 && so >= 8 && so <= 22 && l.d.n >= ctx->tc_min_ofm;
-                    // auto: the tcgen05 kernel where it measured faster than the CUDA-core kernel (profiles/r1_layer_table_int16_b128_tc2_final.json
-                    // against r1_layer_table_int16_b256.json): 3x3 layers up to 52 wide with full 128-channel tiles, deep 1x1 layers up to
-                    // 26 wide; both paths are bit-exact, so mixing them is safe
+                    // auto: the tcgen05 kernel where it measured faster than the CUDA-core kernel (profiles/r2_layer_table_*): every
+                    // 3x3 layer with full 128-channel tiles and >= 64 input channels up to 104 wide, deep 1x1 layers up to 26 wide;
+                    // both paths are bit-exact, so mixing them is safe
                     if (ctx->use_tc < 0 && e == 2 && so >= 8 && so <= 22 &&
-                        ((l.d.size == 3 && l.d.w <= 52 && l.d.n % 128 == 0 && l.d.c >= 128) ||
+                        ((l.d.size == 3 && l.d.w <= 104 && l.d.n % 128 == 0 && l.d.c >= 64) ||
                          (l.d.size == 1 && l.d.w <= 26 && l.d.n >= 256 && l.d.c >= 512)))
                         l.tc = true;
                     if (l.tc) {
@@ -943,6 +982,37 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
         } else if (l.d.type == YOLO2CUDA_REGION) {
             l.region_q = current_qa;
             net->region_q = current_qa;
+        }
+    }
+    // ---- largest-|activation| slots (int16): tensors joined by max-pool / reorg / concat form one class ----
+    if (e == 2) {
+        const int nt = (int)net->T.size();
+        std::vector<int> parent(nt);
+        for (int t = 0; t < nt; ++t) parent[t] = t;
+        auto find = [&](int t) { while (parent[t] != t) t = parent[t] = parent[parent[t]]; return t; };
+        for (size_t i = 0; i < net->L.size(); ++i) {
+            const int ty = net->L[i].d.type;
+            if ((ty == YOLO2CUDA_MAXPOOL || ty == YOLO2CUDA_REORG) && net->tensor_in[i] >= 0 && net->tensor_out[i] >= 0)
+                parent[find(net->tensor_out[i])] = find(net->tensor_in[i]);
+        }
+        net->xslot.assign(nt, 0);
+        net->xknown.assign(nt, 1);
+        for (int t = 0; t < nt; ++t) net->xslot[t] = find(t);
+        net->xknown[find(0)] = 0;                          // the quantised input frames: no maximum is tracked
+        for (size_t i = 0; i < net->L.size(); ++i) {
+            const LayerPlan &l = net->L[i];
+            if (l.d.type != YOLO2CUDA_CONV || net->tensor_out[i] < 0) continue;
+            const bool tracks = l.fast && !l.tc32;          // conv_i16_c4_kernel and conv_i16_tc2_kernel leave their maximum behind
+            if (!tracks) net->xknown[net->xslot[net->tensor_out[i]]] = 0;
+        }
+        for (size_t i = 0; i < net->L.size(); ++i) {
+            LayerPlan &l = net->L[i];
+            if (l.d.type != YOLO2CUDA_CONV) continue;
+            const int si = net->xslot[net->tensor_in[i]], so_ = net->xslot[net->tensor_out[i]];
+            l.cp.xmax_in = net->xknown[si] ? net->d_xmax + si : nullptr;
+            l.cp.xmax_out = net->d_xmax + so_;
+            l.cp.tc_stats = ctx->d_tc_stats;
+            l.cp.tc_force_exact = ctx->tc_force_exact;
         }
     }
     CUDA_OK(ctx, cudaGetLastError());

@@ -58,6 +58,11 @@ struct ConvFastParams {
     int GS;                // groups per pipeline stage
     int so, sb;            // effective shift_out in [8,30]; raw shift_bias
     int leaky;
+    // largest |value| bookkeeping for the tcgen05 kernel's no-saturation fast path (int16 only; both may be NULL):
+    const int *xmax_in;    // device scalar: upper bound of |x| over the input tensor (NULL = unknown, 32768 is assumed)
+    int *xmax_out;         // device scalar the kernel atomicMax-es the largest |output| into
+    unsigned long long *tc_stats;   // device [2]: warp-tiles through the fast / the exact path of the tcgen05 kernel (NULL = not counted)
+    int tc_force_exact;    // tests: the tcgen05 kernel never takes the fast path
 };
 
 // ---- launchers (defined in the .cu files; all asynchronous on `st`) ---------------------------

@@ -233,22 +233,35 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
         __syncthreads();
     }
 
-    if (!active) return;
-    if (mb * kCM + wm * kTMC >= p.OFM) return;
-    int16_t *out = static_cast<int16_t *>(p.out) + (size_t)f * p.out_frame_stride +
-                   (((size_t)(mb * (kCM / 4) + wm) * p.H + y) * p.W + sx * TP) * 4;
+    // largest |output| of the layer for the consumer's no-saturation bound (csrc/conv_i16_tc2.cu): warp -> CTA -> one global atomic
+    __shared__ int s_amax;
+    const bool track = p.xmax_out != nullptr;          // uniform
+    if (track && tid == 0) s_amax = 0;
+    int amax = 0;
+    if (active && mb * kCM + wm * kTMC < p.OFM) {
+        int16_t *out = static_cast<int16_t *>(p.out) + (size_t)f * p.out_frame_stride +
+                       (((size_t)(mb * (kCM / 4) + wm) * p.H + y) * p.W + sx * TP) * 4;
 #pragma unroll
-    for (int q = 0; q < TP; ++q) {
-        if (sx * TP + q >= p.W) break;
-        int v[kTMC];
+        for (int q = 0; q < TP; ++q) {
+            if (sx * TP + q >= p.W) break;
+            int v[kTMC];
 #pragma unroll
-        for (int c = 0; c < kTMC; ++c) {
-            int a = (SCALED ? (acc[c][q] >> k2) : acc[c][q]) - 32768;
-            if (p.leaky && a < 0) a = a / 10;  // C division, truncates toward zero
-            v[c] = a & 0xffff;
+            for (int c = 0; c < kTMC; ++c) {
+                int a = (SCALED ? (acc[c][q] >> k2) : acc[c][q]) - 32768;
+                if (p.leaky && a < 0) a = a / 10;  // C division, truncates toward zero
+                amax = max(amax, a < 0 ? -a : a);
+                v[c] = a & 0xffff;
+            }
+            uint2 o = make_uint2((unsigned)v[0] | ((unsigned)v[1] << 16), (unsigned)v[2] | ((unsigned)v[3] << 16));
+            *reinterpret_cast<uint2 *>(out + q * 4) = o;
         }
-        uint2 o = make_uint2((unsigned)v[0] | ((unsigned)v[1] << 16), (unsigned)v[2] | ((unsigned)v[3] << 16));
-        *reinterpret_cast<uint2 *>(out + q * 4) = o;
+    }
+    if (track) {
+        __syncthreads();                               // s_amax = 0 is visible (every thread of the CTA gets here)
+        amax = __reduce_max_sync(0xffffffffu, amax);
+        if (lane == 0 && amax > 0) atomicMax(&s_amax, amax);
+        __syncthreads();
+        if (tid == 0 && s_amax > 0) atomicMax(p.xmax_out, s_amax);
     }
 }
 

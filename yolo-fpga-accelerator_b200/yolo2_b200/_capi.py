@@ -43,6 +43,7 @@ SYMBOLS = {
     "yolo2cuda_last_error": (C.c_char_p, [C.c_void_p]),
     "yolo2cuda_launch_count": (C.c_uint64, [C.c_void_p]),
     "yolo2cuda_last_kernel": (C.c_char_p, [C.c_void_p]),
+    "yolo2cuda_tc_path_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]),
     "yolo2cuda_layer_host": (C.c_int, _LAYER_ARGS),
     "yolo2cuda_layer_dev": (C.c_int, _LAYER_ARGS),
     "yolo2cuda_quantize_input_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),

@@ -56,6 +56,12 @@ class Accelerator:
     def launch_count(self):
         return int(self.lib.yolo2cuda_launch_count(self.ctx))
 
+    def tc_path_counts(self, reset: bool = False):
+        """(fast, exact): (warp, tile) units of the tcgen05 conv kernel through its no-saturation fast path / its exact step"""
+        f, x = C.c_uint64(0), C.c_uint64(0)
+        _capi.check(self.ctx, self.lib.yolo2cuda_tc_path_counts(self.ctx, C.byref(f), C.byref(x), int(reset)))
+        return int(f.value), int(x.value)
+
     @property
     def last_kernel(self):
         return self.lib.yolo2cuda_last_kernel(self.ctx).decode()
