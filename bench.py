@@ -155,7 +155,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=728)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="STRONG scaling: this many frames per step in total, sharded over the ranks (BASELINE configs[4]: 1024); "
+                         "0 = weak scaling with --frames-per-gpu frames on every rank")
     ap.add_argument("--chunk", type=int, default=0, help="frames per device pass; 0 = the wave-filling size from model.best_pass_size")
+    ap.add_argument("--precision", default="int16", choices=["int16", "fp32"],
+                    help="int16 = the BASELINE metric (default); fp32 = the reference's float build (BASELINE configs[1]) as a secondary line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the region-tensor check against the checker after the timed region")
     ap.add_argument("--ref-procs", type=int, default=0)
@@ -181,10 +186,18 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W = max(args.warmup, 3)   # timing rule: at least 3 warm-up steps
     K = args.steps
-    B = args.frames_per_gpu
+    from yolo2_b200.dist import shard_bounds
+    strong = args.global_batch > 0
+    if strong:
+        lo, hi = shard_bounds(args.global_batch, world, rank)
+        B, total_frames = hi - lo, args.global_batch
+    else:
+        B, total_frames = args.frames_per_gpu, world * args.frames_per_gpu
+    Bmax = -(-total_frames // world)          # largest shard (gather buffers are sized for it)
 
     net = ycfg.parse_network_cfg(cfg_text())
-    pack = yw.synth_pack(net, "int16", seed=0, table="default")
+    fp32 = args.precision == "fp32"
+    pack = yw.synth_pack(net, args.precision, seed=0, table="default")
     chunk = args.chunk if args.chunk > 0 else best_pass_size(net, 128, 400)
     y = Yolo2Net(net, pack, device=local, max_batch=min(chunk, B))
     # run everything on one explicit torch stream so torch.cuda.Event brackets the library's launches
@@ -198,7 +211,21 @@ def main():
     dev_frames = host_frames.cuda(non_blocking=True)                     # 2 MB/frame: 266 MB at B=128 (> 126 MB L2)
     dev_region = torch.empty((B, y.region_outputs), dtype=torch.float32, device="cuda")
     host_region = torch.empty((B, y.region_outputs), dtype=torch.float32).pin_memory()
-    gathered = [torch.empty_like(dev_region) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # The only collective: the final gather of the DETECTIONS (north_star) - boxes + per-class NMS run on every rank's own GPU
+    # (detect_kernel), the survivors are compacted to fixed-size records (compact_detections_kernel: 256 x 32 B + a count per
+    # frame instead of a 287 KB region tensor) and gathered on rank 0.
+    from yolo2_b200.model import compact_detections_gpu, region_detections_gpu
+    DET_CAP, DET_THRESH, DET_NMS = 256, 0.5, 0.45
+    payload = torch.zeros((Bmax, DET_CAP * 8 + 1), dtype=torch.int32, device="cuda")
+    gathered = [torch.empty_like(payload) for _ in range(world)] if (world > 1 and rank == 0) else None
+    det_state = {}
+
+    def detect_and_pack():
+        boxes, probs, obj = region_detections_gpu(y.accel, net, dev_region, net.w, net.h, DET_THRESH, DET_NMS)
+        rec, cnt = compact_detections_gpu(y.accel, boxes, probs, obj, cap=DET_CAP)
+        payload[:B, :DET_CAP * 8] = rec.view(B, -1)
+        payload[:B, DET_CAP * 8] = cnt
+        det_state["counts"] = cnt
 
     def barrier():
         if world > 1:
@@ -207,8 +234,9 @@ def main():
 
     def step_resident():
         y.forward_ptr(dev_frames.data_ptr(), B, dev_region.data_ptr(), device=True)
-        if world > 1:   # the only collective: final gather of the region tensors (north_star)
-            dist.gather(dev_region, gathered, dst=0)
+        if world > 1:
+            detect_and_pack()
+            dist.gather(payload, gathered, dst=0)
 
     def step_e2e():
         y.forward_ptr(host_frames.data_ptr(), B, host_region.data_ptr(), device=False)
@@ -237,7 +265,7 @@ def main():
     ms_dev, ms_wall = timed(step_resident, K)
     launches = y.accel.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
-    value = world * B * K / (ms_dev * 1e-3)
+    value = total_frames * K / (ms_dev * 1e-3)
 
     # per-kernel roofline: CUDA events around every layer of one more (untimed) step
     y.layer_times()
@@ -250,10 +278,13 @@ def main():
     # (csrc/capi.cu auto policy: full 128-channel tiles, >= 128 input channels, <= 52 wide); ~70 % of the device time in the
     # ncu launch list of this command (profiles/r1_bench_launches_ncu.csv)
     def on_tc2(l):
-        return l.type == ycfg.CONV and l.size == 3 and l.n % 128 == 0 and l.c >= 128 and l.w <= 52 and os.environ.get("YOLO2CUDA_TC", "") == ""
-    dom = [(i, l) for i, l in enumerate(net.layers) if on_tc2(l)]
-    dom_name = "conv_i16_tc2_kernel<3,14> (tcgen05.mma kind::i8 + exact CUDA-core round-and-saturate; 3x3 layers <= 52 wide)"
-    if not dom:   # YOLO2CUDA_TC forced: fall back to "all 3x3 conv layers"
+        return l.type == ycfg.CONV and l.size == 3 and l.n % 128 == 0 and l.c >= 64 and l.w <= 104 and os.environ.get("YOLO2CUDA_TC", "") == ""
+    dom = [(i, l) for i, l in enumerate(net.layers) if on_tc2(l)] if not fp32 else []
+    dom_name = "conv_i16_tc2_kernel<3,14> (tcgen05.mma kind::i8 + exact CUDA-core round-and-saturate; 3x3 layers <= 104 wide)"
+    if fp32:
+        dom = [(i, l) for i, l in enumerate(net.layers) if l.type == ycfg.CONV and l.size == 3]
+        dom_name = "conv_f32_c4_kernel<*,3> (FFMA, all 3x3 conv layers)"
+    elif not dom:   # YOLO2CUDA_TC forced: fall back to "all 3x3 conv layers"
         dom = [(i, l) for i, l in enumerate(net.layers) if l.type == ycfg.CONV and l.size == 3]
         dom_name = "all 3x3 conv layers (YOLO2CUDA_TC=%s)" % os.environ.get("YOLO2CUDA_TC")
     dom_ms = float(sum(lt[i] for i, _ in dom))
@@ -266,24 +297,33 @@ def main():
     peaks, peak_src = load_peaks()
     int8_peak_tops = 2.0 * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])   # kernel timed inside a long step
     achieved_tops = dom_macs * 8 * last_chunk / (dom_ms * 1e-3) / 1e12               # 4 int8 MACs per int16 MAC, 2 OP each
+    if fp32:
+        sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        int8_peak_tops = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12        # FFMA: 128 lanes/clk/SM, 2 FLOP each (nominal; MEASURED_PEAKS.json has no fp32 entry)
+        achieved_tops = dom_macs * 2 * last_chunk / (dom_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": dom_name, "achieved": achieved_tops,
                 "peak": int8_peak_tops, "unit": "TFLOP/s", "frac": achieved_tops / int8_peak_tops,
-                "peak_source": f"2 x bf16_tflops_sustained of {peak_src} MEASURED_PEAKS.json (int8 dense = 2 x bf16)",
+                "peak_source": (f"2 x bf16_tflops_sustained of {peak_src} MEASURED_PEAKS.json (int8 dense = 2 x bf16)" if not fp32 else
+                                "nominal fp32 FFMA rate 148 SMs x 128 lanes x 2 FLOP x sm_max_mhz (CUDA-core pipe, 'bound' = fp32 pipe; no measured fp32 peak in MEASURED_PEAKS.json)"),
                 "traffic": None, "launches_per_step": len(dom) * chunks, "avg_launch_ms": dom_ms / len(dom),
                 "share_of_step": dom_ms / all_ms,
                 "exact_steps_per_s": dom_steps * last_chunk / (dom_ms * 1e-3),
                 "exact_steps_per_s_all_conv": conv_steps * last_chunk / (conv_ms * 1e-3),
-                "note": "the reference rounds+saturates every 4 MACs (Tn=4), so the bit-exact datapath is bound by the CUDA-core "
-                        "round-and-saturate step (3 SASS instr per step behind the tensor cores for so = 14..16, 4 otherwise; 7 instr / 4.65 T "
-                        "without them): the kernel is bound by the issue slots of the SM sub-partitions (80 % busy in ncu) and the TMEM "
-                        "hand-off round trip, not by the tensor pipe; see DESIGN.md section 4 and "
-                        "profiles/.  A reference built with Tn=32 runs at ~2.9 k frames/s on the Tn=32 variant of the same kernel "
-                        "(profiles/r1_layer_table_int16_b256_tn32.json)"}
+                "note": ("the reference rounds+saturates every 4 MACs (Tn=4), so every one of the 3.695 G steps of a frame needs CUDA-core "
+                         "work beside the tensor cores: 2 SASS instr per step on the no-saturation fast path (range-checked per K-block, "
+                         "exact 4-instr step otherwise), and the kernel is bound by the issue slots of the SM sub-partitions (75 % busy in "
+                         "ncu, profiles/r2_conv_i16_tc2_ncu_full_summary.csv) and the TMEM hand-off, not by the tensor pipe (35 % busy); "
+                         "DESIGN.md section 4.  A reference built with Tn=32 runs at ~2.9 k frames/s on the Tn=32 variant of the same "
+                         "kernel (profiles/r1_layer_table_int16_b256_tn32.json)") if not fp32 else
+                        "fp32 build of the reference (hls/core/core_compute.cpp:121-172): plain FFMA chains on the CUDA cores"}
+    if not fp32:
+        fast_tiles, exact_tiles = y.accel.tc_path_counts()
+        roofline["tc_fast_path_share"] = fast_tiles / max(1, fast_tiles + exact_tiles)
 
     for _ in range(2):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, K)
-    e2e_value = world * B * K / (ms_e2e * 1e-3)
+    e2e_value = total_frames * K / (ms_e2e * 1e-3)
     frame_bytes = net.c * net.h * net.w * 4
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * y.region_outputs * 4}
 
@@ -300,28 +340,32 @@ def main():
         cores = os.cpu_count() or 1
         if world > 1:
             os.environ["OMP_NUM_THREADS"] = str(max(1, cores // (2 * world)))
-        want, kind = reference_frames(cfg_text(), "int16", 0, "default", 1000 + 8 * rank, sorted({q % 8 for q in pos}),
+        want, kind = reference_frames(cfg_text(), args.precision, 0, "default", 1000 + 8 * rank, sorted({q % 8 for q in pos}),
                                       keep_layers=False, procs=4 if world == 1 else 2)
         got_dev = dev_region.cpu().numpy()
         got_host = host_region.numpy()
         bad = 0
         for q in pos:
+            if fp32:      # BASELINE: within 1e-4 for the float path (region values are probabilities / offsets of O(1))
+                bad += int(np.abs(got_dev[q] - want[q % 8][0]).max() > 1e-4) + int(np.abs(got_host[q] - want[q % 8][0]).max() > 1e-4)
+                continue
             w = want[q % 8][0].view(np.uint32)
             bad += int(not np.array_equal(got_dev[q].view(np.uint32), w)) + int(not np.array_equal(got_host[q].view(np.uint32), w))
         tot = torch.tensor([bad, len(pos)], device="cuda", dtype=torch.int64)
         if world > 1:
             dist.all_reduce(tot)
         parity = {"frames": int(tot[1]), "mismatches": int(tot[0]), "checker": kind, "positions_rank0": pos,
-                  "what": "region tensor of the resident step (device) and of the end-to-end step (host), bit for bit"}
+                  "what": "region tensor of the resident step (device) and of the end-to-end step (host), " +
+                          ("bit for bit" if not fp32 else "max |diff| <= 1e-4")}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         cores = os.cpu_count() or 1
         procs = max(1, min(cores, args.cpu_procs or 32))
-        if orc.have_ref("int16"):
+        if orc.have_ref(args.precision):
             from oracle.ref_driver import time_reference_cpu
-            fps, spf, wall = time_reference_cpu(cfg_text(), "int16", procs=procs, frames_per_proc=1)
+            fps, spf, wall = time_reference_cpu(cfg_text(), args.precision, procs=procs, frames_per_proc=1)
             cpu_baseline = {"value": fps, "unit": UNIT, "cores": procs, "kind": "reference",
                             "seconds_per_frame_per_core": spf, "host_cores": cores,
                             "sample": f"{procs} processes x 1 full 416 COCO frame through unmodified YOLO2_FPGA (layer loop only)"}
@@ -335,19 +379,27 @@ def main():
                             "sample": "oracle port, 1 full 416 COCO frame (OpenMP over output channels)"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int16", "data": "synthetic",
-                "config": {"workload": f"YOLOv2 COCO 416x416 INT16 frame stream (BASELINE configs[4]), {B} frames/GPU/step, "
-                                       f"device passes of {y.max_batch} frames",
-                           "global_batch": world * B, "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+        line = {"metric": METRIC if not fp32 else "YOLOv2-416 FP32 frames/sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+                "dtype": "int16" if not fp32 else "f32", "data": "synthetic",
+                "config": {"workload": (f"YOLOv2 COCO 416x416 {'INT16' if not fp32 else 'FP32'} frame stream (BASELINE configs[{4 if not fp32 else 1}]), " +
+                                        (f"global batch {total_frames} sharded over the ranks ({B} frames on rank 0), " if strong else f"{B} frames/GPU/step, ") +
+                                        f"device passes of {y.max_batch} frames"),
+                           "global_batch": total_frames,
+                           "parallelism": f"frames sharded over {world} GPU(s), no data-path collective" +
+                                          ("; detections (boxes + NMS on each GPU, 8 KB of records per frame) gathered on rank 0 over NCCL" if world > 1 else ""),
                            "l2": f"inputs {B * frame_bytes >> 20} MiB per step > 126 MB L2 (no flush needed)",
-                           "weights": "seeded synthetic int16, Qw=14 Qb=10 Qa=10"},
+                           "weights": "seeded synthetic int16, Qw=14 Qb=10 Qa=10" if not fp32 else "seeded synthetic fp32"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "ms_per_step_wall": ms_wall / K,
                 "parity_checked": parity["frames"] if parity else 0, "parity": parity,
                 "fps_per_gpu": value / world, "exact_steps_per_s_per_gpu": value / world * STEPS_PER_FRAME,
                 "int8_tensor_equiv_frac": value / world * INT8_OP_PER_FRAME / (int8_peak_tops * 1e12)}
+        if fp32:
+            for k in ("exact_steps_per_s_per_gpu", "int8_tensor_equiv_frac"):
+                line.pop(k)
+        if world > 1 and gathered is not None:
+            line["gathered_detections"] = int(sum(int(g[:, DET_CAP * 8].sum()) for g in gathered))
         emit_result(line)
     y.close()
     if world > 1:

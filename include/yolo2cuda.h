@@ -203,6 +203,13 @@ int yolo2cuda_region_detections_dev(yolo2cuda_ctx *ctx, const float *region, int
                                     const float *anchors_host, int im_w, int im_h, int net_w, int net_h,
                                     float thresh, float nms, float *boxes, float *probs, float *objectness);
 
+/* Compacts the positional output of yolo2cuda_region_detections_dev into fixed-size records per frame (DEVICE pointers, async):
+ * records [batch][cap][8] 32-bit words = {entry (cell * n + anchor), class, probability, x, y, w, h, objectness} (the floats as
+ * their bit patterns), ordered by (entry, class); counts [batch] = surviving (entry, class) pairs of the frame (the first `cap`
+ * are stored).  This is what a multi-GPU host gathers instead of the 287 KB region tensors. */
+int yolo2cuda_compact_detections_dev(yolo2cuda_ctx *ctx, const float *boxes, const float *probs, const float *objectness, int batch,
+                                     int total, int classes, int cap, uint32_t *records, int32_t *counts);
+
 #ifdef __cplusplus
 }
 #endif

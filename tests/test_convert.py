@@ -117,8 +117,15 @@ def test_route_q_mismatch_is_harmonised(thin_net, tmp_path):
     with the raw table it does not"""
     from yolo2_b200.model import Yolo2Net
     layers = _fake_darknet(thin_net, 9)
-    layers[19].weights *= np.float32(1.0 / 16)            # conv 19 = layer 24
-    layers[19].biases *= np.float32(1.0 / 16)
+    def scale_output(d, g):                                # folded conv output x g (through the batch-norm gain when there is one)
+        if d.scales is not None:
+            d.scales = d.scales * np.float32(g)
+        else:
+            d.weights = d.weights * np.float32(g)
+        d.biases = d.biases * np.float32(g)
+    scale_output(layers[12], 64.0)                        # conv 12 = layer 16 (the route source): large outputs, low Q
+    scale_output(layers[13], 1.0 / 64)                    #   ... the main branch is brought back to its usual range by the next conv
+    scale_output(layers[19], 1.0 / 16)                    # conv 19 = layer 24 (the skip conv): small outputs, Q at the cap
     folded = convert.fold_batchnorm(layers)
     fp32 = convert.make_fp32_pack(thin_net, folded)
     frames = yw.synth_frames(thin_net, 2, seed=78)

@@ -666,3 +666,66 @@ def test_detection_stream_608_uses_host_tail(oracle):
         region, _ = oracle.net_forward(net, oracle.letterbox_u8(imgs[f], 608, 608), pack)
         wb, wp, wo = oracle.region_boxes_nms(region, l.w, l.h, l.n, l.classes, l.anchors, 160, 90, net.w, net.h, 0.05, 0.45)
         assert _det_set(boxes[f], probs[f]) == _det_set(wb, wp)
+
+
+@pytest.mark.parametrize("q", [0, 7, 10, 15])
+def test_quantizer_boundaries_bit_exact(q, accel16, oracle):
+    """the quantiser without the 64-bit llroundf (trunc + exact tie test): every half-way value k + 0.5 and its two binary32
+    neighbours over the whole int16 range, the values just below 0.5, saturation, infinities, NaN, denormals, random floats"""
+    import ctypes as C
+    import torch
+    k = np.arange(-33000, 33001, dtype=np.float64) + 0.5
+    cand = np.concatenate([k, k - 0.5, np.array([0.49999997, -0.49999997, 0.5, -0.5, 1e30, -1e30, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 0.0, -0.0])])
+    v = (cand * 2.0 ** -q).astype(np.float32)
+    v = np.concatenate([v, np.nextafter(v, np.float32(np.inf)), np.nextafter(v, np.float32(-np.inf)),
+                        np.random.default_rng(q).normal(0, 3000 * 2.0 ** -q, 200000).astype(np.float32)])
+    v = np.ascontiguousarray(np.resize(v, (v.size + 3) // 4 * 4))
+    want = oracle.quantize_input(v, q)
+    dx = torch.from_numpy(v).cuda()
+    dq = torch.empty(v.size, dtype=torch.int16, device="cuda")
+    assert accel16.lib.yolo2cuda_quantize_input_dev(accel16.ctx, C.c_void_p(dx.data_ptr()), C.c_void_p(dq.data_ptr()), v.size, q) == 0
+    accel16.synchronize()
+    got = dq.cpu().numpy()
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, (v[bad[:5]], got[bad[:5]], want[bad[:5]])
+
+
+def test_gpu_detections_tie_order(accel16, oracle):
+    """equal class probabilities + overlapping boxes: detect_kernel must resolve the ties like do_nms_sort's carried-over stable
+    sort (src/core/yolo_post.cpp:70-74), i.e. by the probabilities of the previously processed classes, then scan order"""
+    import torch
+    from test_host_logic import _tied_region
+    from yolo2_b200.model import region_detections_gpu
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 6))
+    l = net.layers[-1]
+    region = np.stack([_tied_region(s) for s in range(4)])
+    gb, gp, go = region_detections_gpu(accel16, net, torch.from_numpy(region).cuda(), 640, 480, 0.1, 0.45)
+    gb, gp = gb.cpu().numpy(), gp.cpu().numpy()
+    for f in range(4):
+        wb, wp, wo = oracle.region_boxes_nms(region[f], l.w, l.h, l.n, l.classes, l.anchors, 640, 480, net.w, net.h, 0.1, 0.45)
+        assert _det_set(gb[f], gp[f]) == _det_set(wb, wp), f
+
+
+def test_compact_detections_records(accel16, oracle):
+    """compact_detections_kernel: the surviving (entry, class) pairs of detect_kernel's positional output as ordered fixed-size
+    records (what the multi-GPU bench gathers instead of region tensors), against numpy"""
+    import torch
+    from test_host_logic import _tied_region
+    from yolo2_b200.model import compact_detections_gpu, region_detections_gpu
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 6))
+    region = np.stack([_tied_region(s) for s in range(3)])
+    gb, gp, go = region_detections_gpu(accel16, net, torch.from_numpy(region).cuda(), 640, 480, 0.1, 0.45)
+    for cap in (4096, 50):
+        rec, cnt = compact_detections_gpu(accel16, gb, gp, go, cap=cap)
+        rec, cnt = rec.cpu().numpy(), cnt.cpu().numpy()
+        b, p, o = gb.cpu().numpy(), gp.cpu().numpy(), go.cpu().numpy()
+        for f in range(3):
+            e, c = np.nonzero(p[f] > 0)
+            assert cnt[f] == len(e) > 100
+            k = min(cap, len(e))
+            want = np.zeros((k, 8), np.uint32)
+            want[:, 0], want[:, 1] = e[:k], c[:k]
+            want[:, 2] = p[f][e[:k], c[:k]].view(np.uint32)
+            want[:, 3:7] = b[f][e[:k]].view(np.uint32)
+            want[:, 7] = o[f][e[:k]].view(np.uint32)
+            assert np.array_equal(rec[f, :k].view(np.uint32), want)

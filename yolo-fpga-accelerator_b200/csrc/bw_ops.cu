@@ -165,15 +165,17 @@ __global__ void reorg_hls_planar_kernel(const T *__restrict__ in, T *__restrict_
     out[((long long)oc * oh + y) * owa + x] = v;
 }
 
+// sat16(llround(in * 2^Q)) of the driver's input quantiser (yolo2_model.cpp:265-271: clamp in float, llround = round half AWAY
+// from zero, clamp again) without the 64-bit software llroundf: v - trunc(v) is exact in binary32, so the tie test is exact.
+// NaN: the reference's float clamps pass it through and llround(NaN) is LLONG_MIN on the hosts it runs on -> -32768; fmaxf drops
+// the NaN operand, which gives the same -32768.
 __device__ __forceinline__ int16_t quantize_one(float in, float scale)
 {
-    float v = in * scale;  // yolo2_model.cpp:265-271
-    if (v > 32767.f) v = 32767.f;
-    if (v < -32768.f) v = -32768.f;
-    long long q = llroundf(v);  // round half away from zero
-    if (q > 32767) q = 32767;
-    if (q < -32768) q = -32768;
-    return (int16_t)q;
+    float v = in * scale;
+    v = fminf(fmaxf(v, -32768.f), 32767.f);
+    const float t = truncf(v);
+    const float r = t + ((fabsf(v - t) >= 0.5f) ? copysignf(1.0f, v) : 0.0f);
+    return (int16_t)__float2int_rz(r);
 }
 
 __global__ void quantize_kernel(const float *__restrict__ in, int16_t *__restrict__ out, size_t count, float scale)
@@ -205,6 +207,39 @@ __global__ void frames_to_c4_kernel(const float *__restrict__ frames, T *__restr
     }
     *reinterpret_cast<typename Vec4<T>::type *>(dst + f * dfs + (((long long)g * H + y) * W + x) * 4) =
         *reinterpret_cast<typename Vec4<T>::type *>(v);
+}
+
+// int16, C <= 4, W % 4 == 0, 16-byte aligned frames: one thread = four consecutive pixels of one row - a 16-byte load per channel
+// plane (a warp reads 512 contiguous bytes of each plane) and two 16-byte stores (the warp writes 1 KB contiguous)
+__global__ void frames_to_c4_i16_v4_kernel(const float *__restrict__ frames, int16_t *__restrict__ dst, int B, int C, int H, int W,
+                                           long long dfs, float scale)
+{
+    const int W4 = W >> 2;
+    const long long total = (long long)B * H * W4;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x4 = idx % W4;
+    long long r = idx / W4;
+    const int y = r % H;
+    const int f = r / H;
+    float4 in[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        in[c] = (c < C) ? __ldg(reinterpret_cast<const float4 *>(frames + (((long long)f * C + c) * H + y) * W) + x4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 px[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        unsigned q[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float sv = k == 0 ? in[c].x : k == 1 ? in[c].y : k == 2 ? in[c].z : in[c].w;
+            q[c] = (c < C) ? (unsigned)(unsigned short)quantize_one(sv, scale) : 0u;
+        }
+        px[k] = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
+    }
+    uint4 *o = reinterpret_cast<uint4 *>(dst + f * dfs + ((long long)y * W + 4 * x4) * 4);
+    o[0] = make_uint4(px[0].x, px[0].y, px[1].x, px[1].y);
+    o[1] = make_uint4(px[2].x, px[2].y, px[3].x, px[3].y);
 }
 
 // Source coordinates of the flat-memory reorg (yolo2_model.cpp:112-129 called as
@@ -391,7 +426,9 @@ void launch_frames_to_c4(const float *frames, void *dst, int B, int C, int H, in
                          int elem_bytes, cudaStream_t st)
 {
     long long total = (long long)B * ceil_div(C, 4) * H * W;
-    if (elem_bytes == 2)
+    if (elem_bytes == 2 && C <= 4 && (W & 3) == 0 && ((uintptr_t)frames & 15) == 0 && ((uintptr_t)dst & 15) == 0 && (dfs & 7) == 0)
+        frames_to_c4_i16_v4_kernel<<<blocks_for(total / 4, 256), 256, 0, st>>>(frames, (int16_t *)dst, B, C, H, W, dfs, ldexpf(1.0f, q_in));
+    else if (elem_bytes == 2)
         frames_to_c4_kernel<int16_t><<<blocks_for(total, 256), 256, 0, st>>>(frames, (int16_t *)dst, B, C, H, W, dfs, ldexpf(1.0f, q_in));
     else
         frames_to_c4_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>(frames, (float *)dst, B, C, H, W, dfs, 1.0f);
@@ -560,6 +597,7 @@ __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ r
     __shared__ short s_src[kDetMax];     // sorted position -> entry
     __shared__ float4 s_sbox[kDetMax];
     __shared__ float s_sp[kDetMax];
+    __shared__ float s_obj[kDetMax];
     __shared__ int s_m;
     const int k = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     const int wh = p.lw * p.lh, total = wh * p.n, per = 5 + p.classes;
@@ -592,6 +630,7 @@ __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ r
         }
         s_box[e] = b;
         s_p[e] = pr;
+        s_obj[e] = o;
         if (k == 0) {
             reinterpret_cast<float4 *>(bo)[e] = b;
             oo[e] = o;
@@ -599,14 +638,32 @@ __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ r
     }
     __syncthreads();
     if (p.nms > 0.f) {
-        // do_nms_sort for class k: order the entries with a non-zero probability by probability (descending, entry index breaks ties) ...
+        // do_nms_sort for class k: order the entries with a non-zero probability by probability, descending.  Ties: the reference
+        // sorts ONE list in place class after class with a stable sort (glibc's qsort is a merge sort), so equal probabilities of
+        // class k keep the order the sorts of classes k-1, k-2, ... 0 left: descending probability of class k-1, then k-2, ...,
+        // finally the scan order (entry index).  Those probabilities are the values before any suppression (a class's values are
+        // only zeroed after its own sort), i.e. recomputable from the region tensor; the loop only runs on exact ties.
+        auto prob_of = [&](int e, int c) -> float {
+            const float o = s_obj[e];
+            if (o == 0.f) return 0.f;
+            const int cell = e / p.n, a = e - cell * p.n;
+            const float q = __fmul_rn(o, reg[(size_t)a * per * wh + cell + (size_t)(5 + c) * wh]);
+            return q > p.thresh ? q : 0.f;
+        };
+        auto tie_before = [&](int j, int e) -> bool {
+            for (int c = k - 1; c >= 0; --c) {
+                const float pj = prob_of(j, c), pe = prob_of(e, c);
+                if (pj != pe) return pj > pe;
+            }
+            return j < e;
+        };
         for (int e = tid; e < total; e += blockDim.x) {
             const float pe = s_p[e];
             if (pe == 0.f) continue;
             int rank = 0;
             for (int j = 0; j < total; ++j) {
                 const float pj = s_p[j];
-                rank += (pj > pe) || (pj == pe && j < e);
+                rank += (pj > pe) || (pj == pe && j != e && tie_before(j, e));
             }
             s_src[rank] = (short)e;
             s_sbox[rank] = s_box[e];
@@ -628,6 +685,57 @@ __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ r
         __syncthreads();
     }
     for (int e = tid; e < total; e += blockDim.x) po[(size_t)e * p.classes + k] = s_p[e];
+}
+
+// Positional detect_kernel output -> compact fixed-size records per frame (what leaves the GPU / crosses NVLink instead of
+// 287 KB region tensors): record = {entry (cell * n + anchor), class, probability, x, y, w, h, objectness} as eight 32-bit words,
+// ordered by (entry, class); counts[f] = number of (entry, class) pairs with a surviving probability (may exceed cap: the
+// first cap are stored).  One CTA per frame, ordered block-wide compaction (ballot + prefix), deterministic.
+__global__ void __launch_bounds__(256) compact_detections_kernel(const float *__restrict__ boxes, const float *__restrict__ probs,
+                                                                  const float *__restrict__ objectness, int total, int classes, int cap,
+                                                                  unsigned *__restrict__ records, int *__restrict__ counts)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *po = probs + (size_t)f * total * classes, *bo = boxes + (size_t)f * total * 4, *oo = objectness + (size_t)f * total;
+    unsigned *ro = records + (size_t)f * cap * 8;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    const int n = total * classes;
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + tid;
+        const float pr = i < n ? po[i] : 0.f;
+        const bool keep = pr > 0.f;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        const int pos = before + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < cap) {
+            const int e = i / classes, c = i - e * classes;
+            const float4 b = reinterpret_cast<const float4 *>(bo)[e];
+            unsigned *r = ro + (size_t)pos * 8;
+            r[0] = (unsigned)e; r[1] = (unsigned)c; r[2] = __float_as_uint(pr);
+            r[3] = __float_as_uint(b.x); r[4] = __float_as_uint(b.y); r[5] = __float_as_uint(b.z); r[6] = __float_as_uint(b.w);
+            r[7] = __float_as_uint(oo[e]);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; ++w) t += s_warp[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) counts[f] = s_base;
+}
+
+void launch_compact_detections(const float *boxes, const float *probs, const float *objectness, int B, int total, int classes, int cap,
+                               unsigned *records, int *counts, cudaStream_t st)
+{
+    compact_detections_kernel<<<B, 256, 0, st>>>(boxes, probs, objectness, total, classes, cap, records, counts);
 }
 
 // returns 0 when launched, -1 when the frame has more candidates than the kernel holds

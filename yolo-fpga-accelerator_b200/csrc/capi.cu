@@ -424,6 +424,18 @@ int yolo2cuda_region_detections_dev(yolo2cuda_ctx *ctx, const float *region, int
     return YOLO2CUDA_SUCCESS;
 }
 
+int yolo2cuda_compact_detections_dev(yolo2cuda_ctx *ctx, const float *boxes, const float *probs, const float *objectness, int batch,
+                                     int total, int classes, int cap, uint32_t *records, int32_t *counts)
+{
+    if (!ctx || !boxes || !probs || !objectness || !records || !counts) return YOLO2CUDA_ERROR;
+    if (batch <= 0 || total <= 0 || classes <= 0 || cap <= 0) return fail(ctx, YOLO2CUDA_ERROR, "compact_detections_dev: bad dimensions");
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    launch_compact_detections(boxes, probs, objectness, batch, total, classes, cap, records, counts, ctx->stream);
+    ctx->launches += 1;
+    CUDA_OK(ctx, cudaGetLastError());
+    return YOLO2CUDA_SUCCESS;
+}
+
 }  // extern "C"
 
 // ================================ whole-network executor ========================================

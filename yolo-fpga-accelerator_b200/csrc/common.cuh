@@ -103,6 +103,9 @@ void launch_frames_to_c4(const float *frames, void *dst, int B, int C, int H, in
 int launch_detect(const float *region, float *boxes, float *probs, float *objectness, int B, int lw, int lh, int n, int classes,
                   const float *anchors, int im_w, int im_h, int net_w, int net_h, float thresh, float nms, const double *expf_tab,
                   cudaStream_t st);
+// positional detect output -> [B][cap][8] records + [B] counts (see bw_ops.cu)
+void launch_compact_detections(const float *boxes, const float *probs, const float *objectness, int B, int total, int classes, int cap,
+                               unsigned *records, int *counts, cudaStream_t st);
 // stb u8 [B][ih][iw][ic] -> float [B][ic][net_h][net_w], darknet letterbox (yolo_image.cpp:84-165,178-187), bit-exact
 void launch_letterbox(const unsigned char *src, float *dst, int B, int iw, int ih, int ic, int net_w, int net_h, cudaStream_t st);
 void launch_reorg_driver_planar(const void *in, void *out, int c, int h, int w, int shift, int elem_bytes, cudaStream_t st);

@@ -68,6 +68,8 @@ SYMBOLS = {
                                     [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "yolo2cuda_region_detections_dev": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p] + [C.c_int] * 4 +
                                         [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yolo2cuda_compact_detections_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                   C.c_void_p, C.c_void_p]),
 }
 
 

@@ -167,6 +167,19 @@ def region_detections_gpu(acc: Accelerator, net: _cfg.Network, region, im_w: int
     return boxes, probs, obj
 
 
+def compact_detections_gpu(acc: Accelerator, boxes, probs, obj, cap: int = 256):
+    """Positional detect output (CUDA tensors of region_detections_gpu) -> (records int32 [batch][cap][8], counts int32 [batch]) on the
+    device: {entry, class, prob bits, x, y, w, h, objectness bits} per surviving (entry, class), ordered; see yolo2cuda.h."""
+    import torch
+    B, total, classes = probs.shape
+    records = torch.zeros((B, cap, 8), dtype=torch.int32, device=probs.device)
+    counts = torch.zeros((B,), dtype=torch.int32, device=probs.device)
+    acc.use_torch_stream(probs.device)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _capi.check(acc.ctx, acc.lib.yolo2cuda_compact_detections_dev(acc.ctx, p(boxes), p(probs), p(obj), B, total, classes, cap, p(records), p(counts)))
+    return records, counts
+
+
 def detections_jsonl(boxes: np.ndarray, probs: np.ndarray, width: int, height: int, labels=None, thresh: float = 0.25,
                      source: str = "", frame_index: int = 0, mode: str = "image") -> str:
     """One JSONL record per inference in the format of the reference's board application
