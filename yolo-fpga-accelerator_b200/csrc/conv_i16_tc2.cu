@@ -42,6 +42,8 @@
 //    step (2.5 with the range check) against 4.5 for the exact one.
 #include "common.cuh"
 #include <cstdio>
+#include <cuda.h>            // CUtensorMap + enums only: the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
+#include <cudaTypedefs.h>
 
 namespace y2 {
 
@@ -301,7 +303,6 @@ __device__ long long g_tc2_tl[48 * 16];
 #endif
 
 struct Tc2Params {
-    const uint2 *in;          // C4 input
     int16_t *out;             // C4 output (already offset to the first output group)
     const unsigned char *w;   // [mtile][kblock][128 rows][64 B]
     const unsigned *wnorm;    // [mtile][kblock][128 rows]: sum of |w| over the 28 weights of the row's K-block (fast-path bound)
@@ -311,15 +312,44 @@ struct Tc2Params {
     unsigned long long *stats;   // [0] += warp-tiles through the fast path, [1] += warp-tiles through the exact path (or NULL)
     int force_exact;          // tests: never take the fast path
     int B, H, W, G, OFM;
-    long long in_frame_stride, out_frame_stride;  // elements
+    long long out_frame_stride;  // elements
     int sb, leaky;
-    int nkb;                  // K-blocks = ceil(G*K2/7)
-    int ctab_cap;             // entries reserved for the activation copy table
-    int PW, rows_max, gs_shift;  // staging: smem row pitch (pixels), band rows incl. halo + zero row, log2(groups per chunk)
+    int nkb;                  // K-blocks per work item = ceil(G*K2/7)
+    int HW;                   // H * W
+    int npt, nitems;          // pixel tiles (48 consecutive pixels of the frame-flattened image); work items = npt x channel tiles
+    int gs_shift, nchunks;    // activation staging: log2(groups per chunk), chunks per work item
+    int boxlen, nbox, seg_px; // TMA boxes per (group, frame segment): nbox boxes of boxlen pixels; seg_px = nbox * boxlen
 };
 
+// one 2-D tensor-map box (boxlen x 1 elements of 8 bytes) global -> shared, completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, int c0, int c1, void *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int kProducer = kEpiWarps + kBuilders;   // the fourth warp of the builder warpgroup: TMA producer of the activation runs
+constexpr int kTabSlots = 4;                        // per-item tables live in a ring: the producer runs at most two items ahead of the epilogue
+constexpr int kNumBars = 2 * kWRing + 4 + 3 * kBRing + 4;
+constexpr int kFixedBytes = ((kWRing * kWBytes + kBRing * 2 * kBBytes + kUBytes + kNumBars * 8 + 16 + kTabSlots * kPT * (16 + 8)) + 127) & ~127;
+
+// PERSISTENT kernel (round 2): one CTA per SM walks the work items  item = blockIdx.x + n * gridDim.x  (static round-robin;
+// item = (48-pixel tile, 128-channel tile)).  Tensor memory, the barriers, the operand ring and the rounding row are set up once;
+// every pipeline counter (K-block parity, TMEM buffer, weight ring, activation chunk) runs on ACROSS items, so the producer,
+// the builders and the issuers are already working on item n+1 while the epilogue warps finish item n - the ~14.6 k-cycle
+// per-CTA prologue + pipeline fill of the one-item-per-CTA form is paid once per SM instead of once per item.
+//
+// Activation staging is TENSOR-MAP TMA (cp.async.bulk.tensor.2d, SASS UTMALDG): the C4 tensor is described as
+// [frame][G*H*W] 8-byte pixels; for every (channel group, frame segment) ONE contiguous run of  48 + 2W + 2  pixels
+// (frame-flat pixels pix0 - W - 1 ... pix0 + 47 + W + 1, everything the 3x3 taps of the item's 48 pixels touch) lands in
+// shared memory, so tap (i, j) of pixel q is run[q + i*W + j].  Image borders are a 6-bit validity mask per pixel
+// (3 tap rows | 3 tap columns) applied by the builders; rows of a neighbouring group that the run drags in are masked the same
+// way, and coordinates outside the tensor are zero-filled by the TMA unit.  An item that straddles a frame boundary stages a
+// second run for the next frame.  (A 4-D [frame][G][H][W] map with per-row boxes is not legal for the 13- and 19-wide layers:
+// their 104- / 152-byte rows break the 16-byte global-stride rule, SURVEY.md appendix A.)
 template <int KS, int SO>
-__global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Params p)
+__global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int K2 = KS * KS;
     constexpr int PAD = KS / 2;
@@ -330,7 +360,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
     int4 *sU = reinterpret_cast<int4 *>(sB + kBRing * 2 * kBBytes);   // chain state between tiles
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(sB + kBRing * 2 * kBBytes + kUBytes);
     unsigned long long *w_full = bars, *w_empty = w_full + kWRing, *a_full = w_empty + kWRing, *a_empty = a_full + 2,
-                       *go = a_empty + 2, *mma_done = go + kBRing, *rd_done = mma_done + kBRing;
+                       *go = a_empty + 2, *mma_done = go + kBRing, *rd_done = mma_done + kBRing, *x_full = rd_done + kBRing,
+                       *x_empty = x_full + 2;
     // go[r]: tile r of the current K-block may be issued = its activation tile is built (1 arrival, builder) AND its TMEM buffer
     // it % 5 has been read out by the epilogue of tile it-5 (4 arrivals, one per warp; pre-arrived for the first five tiles).
     // The ring has kR = 12 slots = one K-block, a multiple of the number of issuers (4), epilogue groups (4) and builders: every
@@ -338,28 +369,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
     // could start waiting two phases ahead would see the previous phase's parity and fall through).
     // rd_done[r]: tile r read out by all four warps of its group; the builders wait for it before they rebuild slot r, which keeps
     // mma_done[r] from completing a second phase before a late epilogue warp has tested the first.
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(rd_done + kBRing + 1);
+    // x_full[c & 1] / x_empty[c & 1]: activation chunk c (global chunk counter) has landed (TMA transaction bytes) / has been
+    // left behind by all three builder warps.
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + kNumBars);
     int *s_amax = reinterpret_cast<int *>(tmem_slot + 1);        // largest |output| of this CTA
     unsigned *s_cnt = tmem_slot + 2;                             // [2]: warp-tiles through the fast / the exact path
-    int *pxtab = reinterpret_cast<int *>(tmem_slot + 4);         // [48][4]: smem pixel offset for tap rows 0..2, valid flag
-    int *rowinfo = pxtab + kPT * 4;                              // [32][2]: per staged row slot: first needed column, prefix of the copy table
-    int2 *ctab = reinterpret_cast<int2 *>(rowinfo + 64);         // copy table of one C4 group plane: (global pixel offset, smem pixel offset)
-    uint2 *sX = reinterpret_cast<uint2 *>(ctab + p.ctab_cap);    // 2 chunks x GS groups x rows_max x PW pixels
+    int4 *pxinfo = reinterpret_cast<int4 *>(tmem_slot + 4);      // [slot][48]: (run index of tap (0,0) for even / odd channel groups, tap-row mask | tap-column mask << 3, -)
+    long long *outoff = reinterpret_cast<long long *>(pxinfo + kTabSlots * kPT);   // [slot][48]: output element offset of the pixel's group-0 word, -1 = no such pixel
+    uint2 *sX = reinterpret_cast<uint2 *>(smem + kFixedBytes);   // 2 chunks x GS groups x 2 segments x seg_px pixels
 
     // the warp index through a shuffle: the compiler then knows it (and every TMEM address / role branch derived from it) is warp-uniform
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-    const long long npix = (long long)p.B * p.H * p.W;
-    const long long pix0 = (long long)blockIdx.x * kPT;
-    const int mtile = blockIdx.y;
-    const int zero_slot = p.rows_max - 1;
     const int GS = 1 << p.gs_shift;
-    const int chunk_px = GS * p.rows_max * p.PW;
-    const long long row_first = pix0 / p.W;                      // global row (frame*H + y) of the first pixel
+    const int nloc = (p.nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // work items of this CTA
+    const int total_kb = nloc * p.nkb;                          // K-blocks of this CTA, all items
 
     if (tid == 0) {
         for (int i = 0; i < kWRing; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 4); }
         for (int i = 0; i < kBRing; ++i) mbar_init(&rd_done[i], 4);
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], kIssuers); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], kIssuers); mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], kBuilders); }
         for (int i = 0; i < kBRing; ++i) { mbar_init(&go[i], 5); mbar_init(&mma_done[i], 1); }
         for (int i = 0; i < kBufs; ++i)
             for (int k = 0; k < 4; ++k) mbar_arrive(&go[i]);
@@ -371,60 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int q = tid; q < kPT; q += kThreads) {
-        long long gp = pix0 + q;
-        int valid = gp < npix;
-        long long grow = valid ? gp / p.W : row_first;
-        int x = valid ? (int)(gp - grow * p.W) : 0;
-        int y = (int)(grow % p.H);
-        int rl = (int)(grow - row_first);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            int yin = y + i - PAD;
-            int slot = (valid && i < KS && yin >= 0 && yin < p.H) ? rl + i : zero_slot;
-            pxtab[q * 4 + i] = slot * p.PW + x;
-        }
-        pxtab[q * 4 + 3] = valid;
-    }
     for (int i = tid; i < kBRing * 2 * kBBytes / 4; i += kThreads) reinterpret_cast<unsigned *>(sB)[i] = 0u;
-    // Activation copy table.  Staged row slot s holds global row row_first - PAD + s; only the columns some pixel of this CTA reads
-    // are copied (a CTA's pixels are consecutive, so on wide images it touches a fraction of each row), and the loader walks a
-    // precomputed (source, destination) list instead of doing index arithmetic per element.
-    if (tid == 0) {
-        const long long pix_last = (pix0 + kPT < npix ? pix0 + kPT : npix) - 1;
-        const long long row_last = pix_last / p.W;
-        const int nrow_cta = (int)(row_last - row_first) + 1;
-        const int x_first = (int)(pix0 - row_first * p.W), x_last = (int)(pix_last - row_last * p.W);
-        int total = 0;
-        for (int s = 0; s < p.rows_max - 1; ++s) {
-            int lo = p.W, hi = -1;
-            const long long Rr = row_first - PAD + s;
-            if (Rr >= 0 && Rr < (long long)p.B * p.H)
-                for (int i = 0; i < KS; ++i) {
-                    const int j = s - i;
-                    if (j < 0 || j >= nrow_cta) continue;
-                    const int xa = (j == 0 ? x_first : 0) - PAD, xb = (j == nrow_cta - 1 ? x_last : p.W - 1) + PAD;
-                    lo = min(lo, max(xa, 0));
-                    hi = max(hi, min(xb, p.W - 1));
-                }
-            rowinfo[2 * s] = lo;
-            rowinfo[2 * s + 1] = total;
-            total += hi >= lo ? hi - lo + 1 : 0;
-        }
-        rowinfo[2 * (p.rows_max - 1)] = 0;
-        rowinfo[2 * (p.rows_max - 1) + 1] = total;      // = entries per C4 group plane
-    }
-    __syncthreads();
-    for (int idx = tid; idx < (p.rows_max - 1) * p.W; idx += kThreads) {
-        const int s = idx / p.W, x = idx - s * p.W;
-        const int lo = rowinfo[2 * s], cnt = rowinfo[2 * s + 3] - rowinfo[2 * s + 1];
-        if (x < lo || x >= lo + cnt) continue;
-        const long long Rr = row_first - PAD + s;
-        const long long ff = Rr / p.H;
-        const int yy = (int)(Rr - ff * p.H);
-        ctab[rowinfo[2 * s + 1] + x - lo] = make_int2((int)(ff * (p.in_frame_stride >> 2)) + yy * p.W + x, s * p.PW + PAD + x);
-    }
-    for (int i = tid; i < 2 * chunk_px; i += kThreads) sX[i] = make_uint2(0u, 0u);
     __syncthreads();
     {   // rounding row (k = 28) of every lo-plane activation tile: b = 2^min(7, e) where a*b = 2^e is the constant to inject
         const int e = (SO <= 15) ? SO - 1 : SO - 9;   // `half` into LL, or half/256 into M
@@ -451,11 +426,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             constexpr unsigned long long kBStep = (2 * kBBytes) >> 4, kBPlane = kBBytes >> 4;   // descriptor address units (16 B)
             unsigned elected;
             asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
-            const unsigned char *wsrc = p.w + (size_t)mtile * p.nkb * kWBytes;
+            // weights of global K-block gbn (item gbn / nkb of this CTA, K-block gbn % nkb of that item's channel tile)
+            auto wsrc_of = [&](int gbn) -> const unsigned char * {
+                const int nn = gbn / p.nkb, bb = gbn - nn * p.nkb;
+                const int mt = ((int)blockIdx.x + nn * (int)gridDim.x) / p.npt;
+                return p.w + ((size_t)mt * p.nkb + bb) * kWBytes;
+            };
             if (iw == 0 && elected) {
-                for (int b = 0; b < kWRing && b < p.nkb; ++b) {
+                for (int b = 0; b < kWRing && b < total_kb; ++b) {
                     mbar_expect_tx(&w_full[b], kWBytes);
-                    bulk_g2s(sW + b * kWBytes, wsrc + (size_t)b * kWBytes, kWBytes, &w_full[b]);
+                    bulk_g2s(sW + b * kWBytes, wsrc_of(b), kWBytes, &w_full[b]);
                 }
             }
             // Weights of a K-block: shared memory -> registers -> tensor memory (A operand slot bn & 1), one lane quadrant per issuer
@@ -482,13 +462,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             PROF_DECL
             stage_weights(0);
             int tb = iw % kBufs;                             // TMEM buffer it % 5 of this warp's next tile
-            for (int b = 0; b < p.nkb; ++b) {
+            for (int b = 0; b < total_kb; ++b) {             // b = global K-block counter of this CTA
                 PROF_ADD(4);
-                if (iw == 0 && b >= 1 && b + 2 < p.nkb && elected) {   // the smem slot of block b-1 has been copied to TMEM: refill it with block b+2
+                if (iw == 0 && b >= 1 && b + 2 < total_kb && elected) {   // the smem slot of block b-1 has been copied to TMEM: refill it with block b+2
                     const int s = (b - 1) % kWRing;
                     mbar_wait(&w_empty[s], ((b - 1) / kWRing) & 1);
                     mbar_expect_tx(&w_full[s], kWBytes);
-                    bulk_g2s(sW + s * kWBytes, wsrc + (size_t)(b + 2) * kWBytes, kWBytes, &w_full[s]);
+                    bulk_g2s(sW + s * kWBytes, wsrc_of(b + 2), kWBytes, &w_full[s]);
                 }
                 __syncwarp();
                 mbar_wait(&a_full[b & 1], (b >> 1) & 1);
@@ -516,28 +496,71 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                     tb = (tb + kIssuers) % kBufs;
                     PROF_ADD(3);
                     // after this warp's first tile of block b: the MMAs of block b-1 (whose slot block b+1 takes) are done or about to be
-                    if (j == 0 && b + 1 < p.nkb) stage_weights(b + 1);
+                    if (j == 0 && b + 1 < total_kb) stage_weights(b + 1);
                 }
             }
             PROF_END;
-        } else if (warp < kEpiWarps + kBuilders) {
-            // ===== three builder warps: stage activations (cp.async) and write the block-diagonal activation tiles, a pair at a time =====
-            const int bw = warp - kEpiWarps;
-            const int bt = bw * 32 + lane;              // 0..95
-            constexpr int kBT = kBuilders * 32;
-            const int nchunks = (p.G + GS - 1) >> p.gs_shift;
-            auto stage_chunk = [&](int c) {
-                uint2 *dst = sX + (c & 1) * chunk_px;
-                const int g0 = c << p.gs_shift, ng = min(GS, p.G - g0);
-                const int per_group = rowinfo[2 * (p.rows_max - 1) + 1];
-                const long long plane = (long long)p.H * p.W;
-                for (int idx = bt; idx < ng * per_group; idx += kBT) {
-                    const int gg = idx / per_group;
-                    const int2 e = ctab[idx - gg * per_group];
-                    cp_async8(dst + gg * p.rows_max * p.PW + e.y, p.in + (g0 + gg) * plane + e.x);
+        } else if (warp == kProducer) {
+            // ===== TMA producer: per work item the pixel tables, then the item's activation chunks (GS channel groups each) =====
+            const int halo = (KS == 3) ? p.W + 1 : 0;
+            int gc = 0;                                      // global chunk counter of this CTA
+            for (int n = 0; n < nloc; ++n) {
+                const int item = (int)blockIdx.x + n * (int)gridDim.x;
+                const int pt = item % p.npt;
+                const long long pix0 = (long long)pt * kPT;
+                const int f0 = (int)(pix0 / p.HW);
+                const int pin0 = (int)(pix0 - (long long)f0 * p.HW);
+                const int qsplit = min(kPT, p.HW - pin0);    // pixels q >= qsplit lie in frame f0 + 1
+                const int nseg = (qsplit < kPT && f0 + 1 < p.B) ? 2 : 1;
+                for (int c = 0; c < p.nchunks; ++c, ++gc) {
+                    const int buf = gc & 1;
+                    if (gc >= 2) mbar_wait(&x_empty[buf], ((gc >> 1) - 1) & 1);   // the builders have left the chunk that used this buffer
+                    if (c == 0) {
+                        // Tables of item n (ring slot n & 3), written AFTER the wait above: the builders have then finished item n-2 at least,
+                        // so every epilogue warp has read a tile of item n-3 and is done with the tables of item n-4 (its output store).
+                        // The builders / epilogue warps see them through the x_full -> go -> mma_done barrier chain.
+                        int4 *pi = pxinfo + (n & (kTabSlots - 1)) * kPT;
+                        long long *oo = outoff + (n & (kTabSlots - 1)) * kPT;
+                        for (int q = lane; q < kPT; q += 32) {
+                            const int seg = q >= qsplit;
+                            const int f = f0 + seg;
+                            const int pin = seg ? q - qsplit : pin0 + q;
+                            const bool valid = f < p.B && pin < p.HW;
+                            const int y = pin / p.W, x = pin - y * p.W;
+                            int mask = 0;
+                            if (valid) {
+#pragma unroll
+                                for (int i = 0; i < KS; ++i) {
+                                    if (y + i - PAD >= 0 && y + i - PAD < p.H) mask |= 1 << i;
+                                    if (x + i - PAD >= 0 && x + i - PAD < p.W) mask |= 8 << i;
+                                }
+                            }
+                            const int idx = seg * p.seg_px + (q - seg * qsplit);
+                            const int start = (seg ? 0 : pin0) - halo;              // first pixel of the segment's run, frame-flat
+                            pi[q] = make_int4(idx + (start & 1), idx + ((start + p.HW) & 1), mask, 0);   // even / odd channel group
+                            oo[q] = valid ? (long long)f * p.out_frame_stride + (long long)pin * 4 : -1LL;
+                        }
+                        __syncwarp();
+                    }
+                    const int g0 = c << p.gs_shift, ng = min(GS, p.G - g0);
+                    const int per_group = nseg * p.nbox, nops = ng * per_group;
+                    if (lane == 0) mbar_expect_tx(&x_full[buf], (unsigned)(nops * p.boxlen * 8));
+                    __syncwarp();
+                    for (int o = lane; o < nops; o += 32) {
+                        const int gg = o / per_group, rem = o - gg * per_group;
+                        const int s = rem / p.nbox, bx = rem - s * p.nbox;
+                        // a box must start on a 16-byte boundary of global memory (an unaligned start is an illegal-instruction fault,
+                        // measured): the run starts at the even pixel at or below its first pixel, and the builders index it one
+                        // pixel further when that rounded (the pxinfo entry carries both indices, by parity of the channel group)
+                        const int c0 = ((g0 + gg) * p.HW + (s ? 0 : pin0) - halo) & ~1;
+                        uint2 *dst = sX + (size_t)((((buf << p.gs_shift) + gg) << 1) + s) * p.seg_px + bx * p.boxlen;
+                        tma_load_2d(dst, &tmap, c0 + bx * p.boxlen, f0 + s, &x_full[buf]);
+                    }
                 }
-                asm volatile("cp.async.commit_group;");
-            };
+            }
+        } else {
+            // ===== three builder warps: write the block-diagonal activation tiles from the staged runs, a pair at a time =====
+            const int bw = warp - kEpiWarps;
             // one tile = 28 entries (step slot s, pixel px) = column s*4+px; lane e < 28 owns entry e of BOTH tiles of a pair.
             // The same four hi bytes also go to rows 4s..4s+3 of the DENSE column 28+px (all seven steps of a pixel in one
             // column): the HH MMA then leaves sum_s HH_s there, which is all the fast path needs of that plane.
@@ -545,68 +568,76 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             const int s0 = has ? lane / kPx : 0, p0 = lane - (lane / kPx) * kPx;
             const int off0 = operand_off(s0 * kPx + p0, 4 * s0);
             const int offd = operand_off(kSteps * kPx + p0, 4 * s0);
-            stage_chunk(0);
-            int staged = 0, ready = -1;
+            int rel_gc = 0, have_gc = -1;               // next chunk to hand back to the producer / last chunk known to have landed
+            int gb = 0;                                 // global K-block counter of this CTA
             PROF_DECL
-            for (int b = 0; b < p.nkb; ++b) {
-                PROF_ADD(4);
-                const int c_first = (min(p.G - 1, (b * kSteps) / K2)) >> p.gs_shift;
-                const int c_need = (min(p.G - 1, (b * kSteps + kSteps - 1) / K2)) >> p.gs_shift;
-                if (staged + 1 < nchunks && staged <= c_first) {
-                    bar_sync_named(1, kBT);             // every builder is past K-block b-1: nobody reads chunk staged-1 any more
-                    stage_chunk(staged + 1);
-                    ++staged;
-                }
-                if (ready < c_need) {
-                    if (staged > c_need) asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    bar_sync_named(1, kBT);             // all builder warps see each other's copies
-                    ready = c_need;
-                }
-                PROF_ADD(0);
-                const int sg0 = b * kSteps + s0;
-                const bool live0 = has && sg0 < p.G * K2;
-                const int g0 = live0 ? sg0 / K2 : 0, t0 = sg0 - g0 * K2;
-                const int ti0 = live0 ? t0 / KS : 0, tj0 = live0 ? t0 - ti0 * KS : 0;
-                const uint2 *xs0 = sX + ((g0 >> p.gs_shift) & 1) * chunk_px + (g0 & (GS - 1)) * p.rows_max * p.PW + tj0;
-#pragma unroll
-                for (int jj = 0; jj < kR / 2 / kBuilders; ++jj) {
-                    const int j = bw + jj * kBuilders;      // pair index in the K-block: ring slots 2j, 2j+1
+            for (int n = 0; n < nloc; ++n) {
+                const int4 *pi = pxinfo + (n & (kTabSlots - 1)) * kPT;
+                const int gc0 = n * p.nchunks;
+                for (int b = 0; b < p.nkb; ++b, ++gb) {
                     PROF_ADD(4);
-                    // every warp of the tiles' epilogue groups has READ OUT the previous K-block's tiles of these slots (which implies
-                    // their MMAs have read the operand tiles): see rd_done[] above
-                    if (b >= 1) {
-                        mbar_wait_m<Y2_TC2_WAIT_HELPER>(&rd_done[2 * j], (b - 1) & 1);
-                        mbar_wait_m<Y2_TC2_WAIT_HELPER>(&rd_done[2 * j + 1], (b - 1) & 1);
+                    const int c_first = (min(p.G - 1, (b * kSteps) / K2)) >> p.gs_shift;
+                    const int c_need = (min(p.G - 1, (b * kSteps + kSteps - 1) / K2)) >> p.gs_shift;
+                    while (rel_gc < gc0 + c_first) {    // nobody in this warp reads chunk rel_gc any more (earlier items included)
+                        __syncwarp();
+                        mbar_arrive_if(&x_empty[rel_gc & 1], lane == 0);
+                        ++rel_gc;
                     }
-                    PROF_ADD(1);
-                    PROF_TL(b * kR + 2 * j, 0); PROF_TL(b * kR + 2 * j + 1, 0);
-                    unsigned char *bh = sB + (j * 4) * kBBytes;
-                    if (has) {
-                        unsigned hi0 = 0, lo0 = 0, hi1 = 0, lo1 = 0;
-                        if (live0) {
-                            const uint2 xa = xs0[pxtab[(2 * j * kPx + p0) * 4 + ti0]];
-                            const uint2 xb = xs0[pxtab[((2 * j + 1) * kPx + p0) * 4 + ti0]];
-                            hi0 = __byte_perm(xa.x, xa.y, 0x7531);
-                            lo0 = __byte_perm(xa.x, xa.y, 0x6420);
-                            hi1 = __byte_perm(xb.x, xb.y, 0x7531);
-                            lo1 = __byte_perm(xb.x, xb.y, 0x6420);
-                        }
-                        *reinterpret_cast<unsigned *>(bh + off0) = hi0;
-                        *reinterpret_cast<unsigned *>(bh + kBBytes + off0) = lo0;
-                        *reinterpret_cast<unsigned *>(bh + 2 * kBBytes + off0) = hi1;
-                        *reinterpret_cast<unsigned *>(bh + 3 * kBBytes + off0) = lo1;
-                        if constexpr (kFast) {
-                            *reinterpret_cast<unsigned *>(bh + offd) = hi0;
-                            *reinterpret_cast<unsigned *>(bh + 2 * kBBytes + offd) = hi1;
-                        }
+                    while (have_gc < gc0 + c_need) {
+                        ++have_gc;
+                        mbar_wait(&x_full[have_gc & 1], (have_gc >> 1) & 1);
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    mbar_arrive_if(&go[2 * j], lane == 0);
-                    mbar_arrive_if(&go[2 * j + 1], lane == 0);
-                    PROF_TL(b * kR + 2 * j, 1); PROF_TL(b * kR + 2 * j + 1, 1);
-                    PROF_ADD(2);
+                    PROF_ADD(0);
+                    const int sg0 = b * kSteps + s0;
+                    const bool live0 = has && sg0 < p.G * K2;
+                    const int g0 = live0 ? sg0 / K2 : 0, t0 = sg0 - g0 * K2;
+                    const int ti0 = live0 ? t0 / KS : 0, tj0 = live0 ? t0 - ti0 * KS : 0;
+                    const int need = live0 ? ((1 << ti0) | (8 << tj0)) : 0x40;      // mask bits this lane's tap needs (0x40 is never set)
+                    const int cbuf = (gc0 + (g0 >> p.gs_shift)) & 1;
+                    const bool godd = g0 & 1;
+                    const uint2 *xs0 = sX + (size_t)((((cbuf << p.gs_shift) + (g0 & (GS - 1))) << 1)) * p.seg_px + ti0 * p.W + tj0;
+#pragma unroll
+                    for (int jj = 0; jj < kR / 2 / kBuilders; ++jj) {
+                        const int j = bw + jj * kBuilders;      // pair index in the K-block: ring slots 2j, 2j+1
+                        PROF_ADD(4);
+                        // every warp of the tiles' epilogue groups has READ OUT the previous K-block's tiles of these slots (which implies
+                        // their MMAs have read the operand tiles): see rd_done[] above
+                        if (gb >= 1) {
+                            mbar_wait_m<Y2_TC2_WAIT_HELPER>(&rd_done[2 * j], (gb - 1) & 1);
+                            mbar_wait_m<Y2_TC2_WAIT_HELPER>(&rd_done[2 * j + 1], (gb - 1) & 1);
+                        }
+                        PROF_ADD(1);
+                        PROF_TL(gb * kR + 2 * j, 0); PROF_TL(gb * kR + 2 * j + 1, 0);
+                        unsigned char *bh = sB + (j * 4) * kBBytes;
+                        if (has) {
+                            unsigned hi0 = 0, lo0 = 0, hi1 = 0, lo1 = 0;
+                            const int4 ia = pi[2 * j * kPx + p0], ib = pi[(2 * j + 1) * kPx + p0];
+                            if ((ia.z & need) == need) {
+                                const uint2 xa = xs0[godd ? ia.y : ia.x];
+                                hi0 = __byte_perm(xa.x, xa.y, 0x7531);
+                                lo0 = __byte_perm(xa.x, xa.y, 0x6420);
+                            }
+                            if ((ib.z & need) == need) {
+                                const uint2 xb = xs0[godd ? ib.y : ib.x];
+                                hi1 = __byte_perm(xb.x, xb.y, 0x7531);
+                                lo1 = __byte_perm(xb.x, xb.y, 0x6420);
+                            }
+                            *reinterpret_cast<unsigned *>(bh + off0) = hi0;
+                            *reinterpret_cast<unsigned *>(bh + kBBytes + off0) = lo0;
+                            *reinterpret_cast<unsigned *>(bh + 2 * kBBytes + off0) = hi1;
+                            *reinterpret_cast<unsigned *>(bh + 3 * kBBytes + off0) = lo1;
+                            if constexpr (kFast) {
+                                *reinterpret_cast<unsigned *>(bh + offd) = hi0;
+                                *reinterpret_cast<unsigned *>(bh + 2 * kBBytes + offd) = hi1;
+                            }
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        mbar_arrive_if(&go[2 * j], lane == 0);
+                        mbar_arrive_if(&go[2 * j + 1], lane == 0);
+                        PROF_TL(gb * kR + 2 * j, 1); PROF_TL(gb * kR + 2 * j + 1, 1);
+                        PROF_ADD(2);
+                    }
                 }
             }
             PROF_END;
@@ -616,23 +647,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
         const int q4 = warp & 3, kg = warp >> 2;
         const int row = q4 * 32 + lane;
-        const int m = mtile * kM + row;
         const unsigned lane_base = tmem + ((unsigned)(q4 * 32) << 16);
         int4 *myU = sU + tid;                       // [tile of the group] at stride kEpiWarps * 32
-        {
-            long long bv = (m < p.OFM) ? (long long)p.bias[m] : 0;
-            long long base = round_shift64(bv, p.sb);
-            const long long rb = (1LL << (33 - SO)) + 2;      // |(P + half) >> so| <= 2^(33-so): clamping the bias term there cannot change clamp16(bias + r)
-            long long boff = base + 32768;
-            if (boff > 65535 + rb) boff = 65535 + rb;
-            if (boff < -rb) boff = -rb;
-#pragma unroll
-            for (int r = 0; r < kTPG; ++r) myU[r * kEpiWarps * 32] = make_int4((int)boff, (int)boff, (int)boff, (int)boff);
-        }
+        const unsigned xmax = (kFast && !p.force_exact) ? (p.xmax_in ? (unsigned)min(max(*p.xmax_in, 0), 32768) : 32768u) : 0u;
         // fast-path bound of this channel for one K-block: Dsum >= sum over the block's steps of |rs(P_s, so)|, and the window
         // [Dsum, Dsum + lim] the offset accumulator must lie in for the block to be saturation-free (lim < 0: never)
-        const unsigned *wn = p.wnorm + (size_t)mtile * p.nkb * kM + row;
-        const unsigned xmax = (kFast && !p.force_exact) ? (p.xmax_in ? (unsigned)min(max(*p.xmax_in, 0), 32768) : 32768u) : 0u;
         auto bound_of = [&](unsigned w1, int &dsum, int &lim) {
             const unsigned long long prod = (unsigned long long)w1 * xmax;
             const unsigned long long d = (prod >> SO) + 8;
@@ -641,110 +660,131 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             if (!kFast || p.force_exact || lim < 0) { dsum = 0x40000000; lim = 0; }    // U - dsum < 0 -> the unsigned compare fails
         };
         unsigned nfast = 0, nexact = 0;
+        int amax = 0;
         PROF_DECL
         int tb = kg % kBufs;                        // TMEM buffer it % 5 of this group's next tile (stride kGroups)
-        // the norm of K-block b+1 is LOADED during block b and first USED at the top of block b+1: a global load's latency
-        // (hundreds of cycles) must never sit between a tile becoming ready and its read-out
+        int gb = 0;                                 // global K-block counter of this CTA
+        int mt = (int)blockIdx.x / p.npt;           // channel tile of the current item
+        // loaded one item / one K-block ahead: a global load's latency (hundreds of cycles) must never sit between a tile becoming
+        // ready and its read-out
+        int bias_next = (mt * kM + row < p.OFM) ? (int)p.bias[mt * kM + row] : 0;
+        const unsigned *wn = p.wnorm + (size_t)mt * p.nkb * kM + row;
         unsigned w1_next = wn[0];
-        for (int b = 0; b < p.nkb; ++b) {
-            PROF_ADD(4);
-            int dsum, lim;
-            bound_of(w1_next, dsum, lim);
-            if (b + 1 < p.nkb) w1_next = wn[(size_t)(b + 1) * kM];
-            PROF_ADD(0);
+        for (int n = 0; n < nloc; ++n) {
+            const int m = mt * kM + row;
+            {
+                const long long base = round_shift64((long long)bias_next, p.sb);
+                const long long rb = (1LL << (33 - SO)) + 2;      // |(P + half) >> so| <= 2^(33-so): clamping the bias term there cannot change clamp16(bias + r)
+                long long boff = base + 32768;
+                if (boff > 65535 + rb) boff = 65535 + rb;
+                if (boff < -rb) boff = -rb;
 #pragma unroll
-            for (int rr = 0; rr < kTPG; ++rr) {
-                const int r = kGroups * rr + kg;
+                for (int r = 0; r < kTPG; ++r) myU[r * kEpiWarps * 32] = make_int4((int)boff, (int)boff, (int)boff, (int)boff);
+            }
+            const int mt_next = (n + 1 < nloc) ? ((int)blockIdx.x + (n + 1) * (int)gridDim.x) / p.npt : mt;
+            if (n + 1 < nloc) bias_next = (mt_next * kM + row < p.OFM) ? (int)p.bias[mt_next * kM + row] : 0;
+            const unsigned *wn_next = p.wnorm + (size_t)mt_next * p.nkb * kM + row;
+            for (int b = 0; b < p.nkb; ++b, ++gb) {
                 PROF_ADD(4);
-                mbar_wait_m<Y2_TC2_WAIT_EPI>(&mma_done[r], b & 1);
-                PROF_ADD(1);
-                PROF_TL(b * kR + r, 4 + q4);
-                asm volatile("tcgen05.fence::after_thread_sync;");
-                const unsigned base = lane_base + tb * kBufCols;
-                int mm[32], ll[32], hd[4];       // column n = step*4 + pixel; hd = the dense columns 28..31 of the HH plane
-                tmem_ld28(base + kN, mm);
-                tmem_ld28(base + 2 * kN, ll);
-                if constexpr (kFast) tmem_ld4(base + kSteps * kPx, hd);
-                // while the loads fly: chain state and the saturation-free test
-                const int4 u = myU[rr * kEpiWarps * 32];
-                int U[kPx] = {u.x, u.y, u.z, u.w};
-                bool ok = kFast;
+                int dsum, lim;
+                bound_of(w1_next, dsum, lim);
+                if (b + 1 < p.nkb) w1_next = wn[(size_t)(b + 1) * kM];
+                else if (n + 1 < nloc) w1_next = wn_next[0];
+                PROF_ADD(0);
 #pragma unroll
-                for (int j = 0; j < kPx; ++j) ok = ok && (unsigned)(U[j] - dsum) <= (unsigned)lim;
-                const bool fast = __all_sync(0xffffffffu, ok);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                reg_fence16(mm); reg_fence12(mm + 16); reg_fence16(ll); reg_fence12(ll + 16);
-                if constexpr (kFast) asm volatile("" : "+r"(hd[0]), "+r"(hd[1]), "+r"(hd[2]), "+r"(hd[3])::"memory");   // (on both paths: the
-                                                              // registers of an asynchronous load stay reserved until the wait above)
-                if (fast) {
-                    if constexpr (kFast) {
-                        // everything is in registers: tile it+5 (ring slot r+5 mod 12) may overwrite this TMEM buffer
+                for (int rr = 0; rr < kTPG; ++rr) {
+                    const int r = kGroups * rr + kg;
+                    PROF_ADD(4);
+                    mbar_wait_m<Y2_TC2_WAIT_EPI>(&mma_done[r], gb & 1);
+                    PROF_ADD(1);
+                    PROF_TL(gb * kR + r, 4 + q4);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const unsigned base = lane_base + tb * kBufCols;
+                    int mm[32], ll[32], hd[4];       // column n = step*4 + pixel; hd = the dense columns 28..31 of the HH plane
+                    tmem_ld28(base + kN, mm);
+                    tmem_ld28(base + 2 * kN, ll);
+                    if constexpr (kFast) tmem_ld4(base + kSteps * kPx, hd);
+                    // while the loads fly: chain state and the saturation-free test
+                    const int4 u = myU[rr * kEpiWarps * 32];
+                    int U[kPx] = {u.x, u.y, u.z, u.w};
+                    bool ok = kFast;
+#pragma unroll
+                    for (int j = 0; j < kPx; ++j) ok = ok && (unsigned)(U[j] - dsum) <= (unsigned)lim;
+                    const bool fast = __all_sync(0xffffffffu, ok);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    reg_fence16(mm); reg_fence12(mm + 16); reg_fence16(ll); reg_fence12(ll + 16);
+                    if constexpr (kFast) asm volatile("" : "+r"(hd[0]), "+r"(hd[1]), "+r"(hd[2]), "+r"(hd[3])::"memory");   // (on both paths: the
+                                                                  // registers of an asynchronous load stay reserved until the wait above)
+                    if (fast) {
+                        if constexpr (kFast) {
+                            // everything is in registers: tile it+5 (ring slot r+5 mod 12) may overwrite this TMEM buffer
+                            asm volatile("tcgen05.fence::before_thread_sync;");
+                            __syncwarp();
+                            mbar_arrive_if(&go[r + kBufs < kR ? r + kBufs : r + kBufs - kR], lane == 0);
+                            mbar_arrive_if(&rd_done[r], lane == 0);
+                            PROF_ADD(2);
+                            PROF_TL(gb * kR + r, 8 + q4);
+#pragma unroll
+                            for (int j = 0; j < kPx; ++j) U[j] += hd[j] * (1 << (16 - (SO <= 16 ? SO : 16)));
+#pragma unroll
+                            for (int nn = 0; nn < kSteps * kPx; ++nn) U[nn % kPx] += (mm[nn] * 256 + ll[nn]) >> SO;   // IMAD, LEA.HI.SX32
+                            ++nfast;
+                        }
+                    } else {
+                        // exact path: fold M and LL first, then read the per-step HH columns into the registers LL occupied
+                        if constexpr (SO <= 16) {
+#pragma unroll
+                            for (int nn = 0; nn < kSteps * kPx; ++nn) mm[nn] = mm[nn] * 256 + ll[nn];              // t = 256 M + LL
+                        } else {
+#pragma unroll
+                            for (int nn = 0; nn < kSteps * kPx; ++nn) mm[nn] = mm[nn] + (ll[nn] >> 8);             // M + (LL >> 8)
+                        }
+                        tmem_ld28(base, ll);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        reg_fence16(ll); reg_fence12(ll + 16);
                         asm volatile("tcgen05.fence::before_thread_sync;");
                         __syncwarp();
                         mbar_arrive_if(&go[r + kBufs < kR ? r + kBufs : r + kBufs - kR], lane == 0);
                         mbar_arrive_if(&rd_done[r], lane == 0);
                         PROF_ADD(2);
-                        PROF_TL(b * kR + r, 8 + q4);
 #pragma unroll
-                        for (int j = 0; j < kPx; ++j) U[j] += hd[j] * (1 << (16 - (SO <= 16 ? SO : 16)));
-#pragma unroll
-                        for (int n = 0; n < kSteps * kPx; ++n) U[n % kPx] += (mm[n] * 256 + ll[n]) >> SO;   // IMAD, LEA.HI.SX32
-                        ++nfast;
+                        for (int nn = 0; nn < kSteps * kPx; ++nn) {
+                            int d;
+                            if constexpr (SO <= 16) d = ll[nn] * (1 << (16 - (SO <= 16 ? SO : 16))) + (mm[nn] >> SO);     // 65536 HH is a multiple of 2^so
+                            else d = (ll[nn] * 256 + mm[nn]) >> (SO - 8);
+                            U[nn % kPx] = __viaddmin_s32_relu(U[nn % kPx], d, 65535);   // VIADDMNMX.RELU: max(min(acc + d, 65535), 0)
+                        }
+                        ++nexact;
                     }
-                } else {
-                    // exact path: fold M and LL first, then read the per-step HH columns into the registers LL occupied
-                    if constexpr (SO <= 16) {
-#pragma unroll
-                        for (int n = 0; n < kSteps * kPx; ++n) mm[n] = mm[n] * 256 + ll[n];              // t = 256 M + LL
-                    } else {
-#pragma unroll
-                        for (int n = 0; n < kSteps * kPx; ++n) mm[n] = mm[n] + (ll[n] >> 8);             // M + (LL >> 8)
-                    }
-                    tmem_ld28(base, ll);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    reg_fence16(ll); reg_fence12(ll + 16);
-                    asm volatile("tcgen05.fence::before_thread_sync;");
-                    __syncwarp();
-                    mbar_arrive_if(&go[r + kBufs < kR ? r + kBufs : r + kBufs - kR], lane == 0);
-                    mbar_arrive_if(&rd_done[r], lane == 0);
-                    PROF_ADD(2);
-#pragma unroll
-                    for (int n = 0; n < kSteps * kPx; ++n) {
-                        int d;
-                        if constexpr (SO <= 16) d = ll[n] * (1 << (16 - (SO <= 16 ? SO : 16))) + (mm[n] >> SO);     // 65536 HH is a multiple of 2^so
-                        else d = (ll[n] * 256 + mm[n]) >> (SO - 8);
-                        U[n % kPx] = __viaddmin_s32_relu(U[n % kPx], d, 65535);   // VIADDMNMX.RELU: max(min(acc + d, 65535), 0)
-                    }
-                    ++nexact;
+                    myU[rr * kEpiWarps * 32] = make_int4(U[0], U[1], U[2], U[3]);
+                    tb = (tb + kGroups) % kBufs;
+                    PROF_ADD(3);
+                    PROF_TL(gb * kR + r, 12 + q4);
                 }
-                myU[rr * kEpiWarps * 32] = make_int4(U[0], U[1], U[2], U[3]);
-                tb = (tb + kGroups) % kBufs;
-                PROF_ADD(3);
-                PROF_TL(b * kR + r, 12 + q4);
             }
+            // ---- the item's 12 pixels of this thread's channel: leaky, store, largest |output| ----
+            if (m < p.OFM) {
+                const long long *oo = outoff + (n & (kTabSlots - 1)) * kPT;
+                int16_t *om = p.out + ((long long)(m >> 2) * p.HW * 4 + (m & 3));
+#pragma unroll
+                for (int rr = 0; rr < kTPG; ++rr) {
+                    const int4 u = myU[rr * kEpiWarps * 32];
+                    const int Uo[kPx] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int j = 0; j < kPx; ++j) {
+                        const long long off = oo[(kGroups * rr + kg) * kPx + j];
+                        if (off < 0) continue;
+                        int a = Uo[j] - 32768;
+                        if (p.leaky && a < 0) a = a / 10;
+                        amax = max(amax, a < 0 ? -a : a);
+                        om[off] = (int16_t)a;
+                    }
+                }
+            }
+            mt = mt_next;
+            wn = wn_next;
         }
         PROF_END;
-        int amax = 0;
-        if (m < p.OFM) {
-#pragma unroll
-            for (int rr = 0; rr < kTPG; ++rr) {
-                const int4 u = myU[rr * kEpiWarps * 32];
-                const int Uo[kPx] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int j = 0; j < kPx; ++j) {
-                    const long long gp = pix0 + (kGroups * rr + kg) * kPx + j;
-                    if (gp >= npix) continue;
-                    const long long grow = gp / p.W;
-                    const int x = (int)(gp - grow * p.W);
-                    const long long f = grow / p.H;
-                    const int y = (int)(grow - f * p.H);
-                    int a = Uo[j] - 32768;
-                    if (p.leaky && a < 0) a = a / 10;
-                    amax = max(amax, a < 0 ? -a : a);
-                    p.out[f * p.out_frame_stride + (((long long)(m >> 2) * p.H + y) * p.W + x) * 4 + (m & 3)] = (int16_t)a;
-                }
-            }
-        }
         if (p.xmax_out) {
             amax = __reduce_max_sync(0xffffffffu, amax);
             if (lane == 0) atomicMax(s_amax, amax);
@@ -828,19 +868,19 @@ __global__ void wnorm_tc2_kernel(const int16_t *__restrict__ blob, unsigned *__r
 }
 
 template <int KS, int SO>
-void launch_one(const Tc2Params &p, dim3 grid, size_t smem, cudaStream_t st)
+void launch_one(const Tc2Params &p, const CUtensorMap &tmap, dim3 grid, size_t smem, cudaStream_t st)
 {
     // set on every launch (a microsecond): the attribute is per device and a host may drive several GPUs from several threads,
     // so a cached "already configured" flag would be a data race for nothing
     cudaFuncSetAttribute(conv_i16_tc2_kernel<KS, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    conv_i16_tc2_kernel<KS, SO><<<grid, kThreads, smem, st>>>(p);
+    conv_i16_tc2_kernel<KS, SO><<<grid, kThreads, smem, st>>>(p, tmap);
 }
 
 template <int KS>
-bool dispatch_so(const Tc2Params &p, int so, dim3 grid, size_t smem, cudaStream_t st)
+bool dispatch_so(const Tc2Params &p, const CUtensorMap &tmap, int so, dim3 grid, size_t smem, cudaStream_t st)
 {
     switch (so) {
-#define Y2_TC2_CASE(S) case S: launch_one<KS, S>(p, grid, smem, st); return true;
+#define Y2_TC2_CASE(S) case S: launch_one<KS, S>(p, tmap, grid, smem, st); return true;
         Y2_TC2_CASE(8) Y2_TC2_CASE(9) Y2_TC2_CASE(10) Y2_TC2_CASE(11) Y2_TC2_CASE(12) Y2_TC2_CASE(13) Y2_TC2_CASE(14) Y2_TC2_CASE(15)
         Y2_TC2_CASE(16) Y2_TC2_CASE(17) Y2_TC2_CASE(18) Y2_TC2_CASE(19) Y2_TC2_CASE(20) Y2_TC2_CASE(21) Y2_TC2_CASE(22)
 #undef Y2_TC2_CASE
@@ -873,35 +913,77 @@ void launch_wprep_tc2(const int16_t *blob, void *dst, int ifm, int ofm, int ksiz
                                                                       TM, TN, nkb, rows);
 }
 
-// Returns 1 when launched, -1 when the shape/shift is not eligible for the tensor-core path.
+// the driver's tensor-map encoder without linking libcuda: resolved once through the runtime (thread-safe static initialisation)
+static PFN_cuTensorMapEncodeTiled tensor_map_encoder()
+{
+    static const PFN_cuTensorMapEncodeTiled fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (PFN_cuTensorMapEncodeTiled)f;
+    }();
+    return fn;
+}
+
+// Returns 1 when launched, -1 when the shape/shift is not eligible for the tensor-core path, -2 when the tensor map cannot be built.
 int launch_conv_i16_tc2(const ConvFastParams &cp, int ksize, cudaStream_t st, const char **variant)
 {
     if ((ksize != 1 && ksize != 3) || cp.so < 8 || cp.so > 22) return -1;
     Tc2Params p{};
-    p.in = (const uint2 *)cp.in; p.out = (int16_t *)cp.out; p.w = (const unsigned char *)cp.w; p.bias = (const int16_t *)cp.bias;
+    p.out = (int16_t *)cp.out; p.w = (const unsigned char *)cp.w; p.bias = (const int16_t *)cp.bias;
     p.wnorm = (const unsigned *)((const char *)cp.w + tiles_bytes(cp.G * 4, cp.OFM, ksize));
     p.xmax_in = cp.xmax_in; p.xmax_out = cp.xmax_out; p.stats = cp.tc_stats; p.force_exact = cp.tc_force_exact;
     p.B = cp.B; p.H = cp.H; p.W = cp.W; p.G = cp.G; p.OFM = cp.OFM;
-    p.in_frame_stride = cp.in_frame_stride; p.out_frame_stride = cp.out_frame_stride;
+    p.out_frame_stride = cp.out_frame_stride;
     p.sb = cp.sb; p.leaky = cp.leaky;
     p.nkb = ceil_div(cp.G * ksize * ksize, kSteps);
-    p.PW = cp.W + ksize - 1;
-    // 48 consecutive pixels touch at most ceil(47/W)+1 rows; + halo rows + the zero row
-    p.rows_max = (kPT - 1) / cp.W + 2 + (ksize - 1) + 1;
-    if (p.rows_max > 30) return -1;                     // rowinfo[] holds 32 staged rows
-    p.ctab_cap = (p.rows_max - 1) * cp.W;
-    const size_t fixed = (size_t)kWRing * kWBytes + (size_t)kBRing * 2 * kBBytes + kUBytes + 768 + kPT * 16 + 256 + (size_t)p.ctab_cap * 8;
-    const size_t per_group = (size_t)p.rows_max * p.PW * 8;
-    int gs = (int)((200 * 1024 - fixed) / (2 * per_group));
+    p.HW = cp.H * cp.W;
+    const long long npix = (long long)cp.B * p.HW;
+    const long long npt = (npix + kPT - 1) / kPT;
+    const int mtiles = ceil_div(cp.OFM, kM);
+    if (npt * mtiles > 0x3fffffffLL || (long long)cp.G * p.HW > 0x7fffffffLL - 4096) return -1;
+    p.npt = (int)npt;
+    p.nitems = (int)(npt * mtiles);
+    // a pixel tile may straddle ONE frame boundary (two staged runs); frames smaller than a tile only as a single frame
+    if (p.HW < kPT && cp.B > 1) return -1;
+    // the staged run of one (group, frame segment): every pixel the taps of 48 consecutive pixels touch, in boxes of <= 256 pixels
+    // whose shared-memory destinations stay 128-byte aligned (16 pixels)
+    const int run = kPT + (ksize == 3 ? 2 * cp.W + 2 : 0) + 1;   // + 1: the run starts on an even pixel
+    p.nbox = ceil_div(run, 256);
+    p.boxlen = (ceil_div(run, p.nbox) + 15) & ~15;
+    p.seg_px = p.nbox * p.boxlen;
+    const size_t per_group = (size_t)2 * p.seg_px * 8;
+    int gs = (int)((200 * 1024 - (size_t)kFixedBytes) / (2 * per_group));
     if (gs < 1) return -1;
     int sh = 0;
     while ((2 << sh) <= gs && (2 << sh) <= 16) ++sh;   // largest power of two <= min(gs, 16)
     p.gs_shift = sh;
     gs = 1 << sh;
-    size_t smem = fixed + 2 * per_group * gs + 1024;
+    p.nchunks = ceil_div(cp.G, gs);
+    size_t smem = (size_t)kFixedBytes + 2 * per_group * gs;
     if (smem < 120 * 1024) smem = 120 * 1024;          // one CTA per SM: a CTA allocates all 512 TMEM columns
-    dim3 grid((unsigned)(((long long)cp.B * cp.H * cp.W + kPT - 1) / kPT), ceil_div(cp.OFM, kM));
-    const bool ok = ksize == 3 ? dispatch_so<3>(p, cp.so, grid, smem, st) : dispatch_so<1>(p, cp.so, grid, smem, st);
+    // tensor map over the C4 input as [frame][G*H*W] 8-byte pixels
+    const unsigned long long frame_bytes = cp.B > 1 ? (unsigned long long)cp.in_frame_stride * 2 : (((unsigned long long)cp.G * p.HW * 8 + 15) & ~15ull);
+    if ((frame_bytes & 15) || ((uintptr_t)cp.in & 15) || frame_bytes < (unsigned long long)cp.G * p.HW * 8) return -1;
+    const PFN_cuTensorMapEncodeTiled encode = tensor_map_encoder();
+    if (!encode) return -2;
+    alignas(64) CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cp.G * p.HW, (cuuint64_t)cp.B};
+    const cuuint64_t gstride[1] = {(cuuint64_t)frame_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)p.boxlen, 1u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void *>(cp.in), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return -2;
+    int dev = 0, nsm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm < 1) return -2;
+#ifdef Y2_TC2_GRID
+    nsm = Y2_TC2_GRID;                                  // experiments: fewer / more persistent CTAs than SMs
+#endif
+    dim3 grid((unsigned)(p.nitems < nsm ? p.nitems : nsm));
+    const bool ok = ksize == 3 ? dispatch_so<3>(p, tmap, cp.so, grid, smem, st) : dispatch_so<1>(p, tmap, cp.so, grid, smem, st);
     if (!ok) return -1;
 #ifdef Y2_TC2_PROFILE
     {
