@@ -274,17 +274,15 @@ def main():
     lt = y.layer_times()
     chunks = (B + y.max_batch - 1) // y.max_batch       # layer_times covers the LAST chunk of the step
     last_chunk = B - (chunks - 1) * y.max_batch
-    # dominant kernel = conv_i16_tc2_kernel<3,so> (tcgen05): the 3x3 layers the network executor puts on the tensor cores
-    # (csrc/capi.cu auto policy: full 128-channel tiles, >= 128 input channels, <= 52 wide); ~70 % of the device time in the
-    # ncu launch list of this command (profiles/r1_bench_launches_ncu.csv)
-    def on_tc2(l):
-        return l.type == ycfg.CONV and l.size == 3 and l.n % 128 == 0 and l.c >= 64 and l.w <= 104 and os.environ.get("YOLO2CUDA_TC", "") == ""
-    dom = [(i, l) for i, l in enumerate(net.layers) if on_tc2(l)] if not fp32 else []
-    dom_name = "conv_i16_tc2_kernel<3,14> (tcgen05.mma kind::i8 + exact CUDA-core round-and-saturate; 3x3 layers <= 104 wide)"
+    # dominant kernel = conv_i16_tc2_kernel<3,so> (persistent tcgen05 + TMA kernel): the 3x3 layers the network executor puts on the
+    # tensor cores (csrc/capi.cu auto policy), taken from the kernel name each layer actually ran (Yolo2Net.layer_kernel);
+    # ~85 % of the device time in the ncu launch list of this command (profiles/r2_bench_launches_ncu.csv)
+    dom = [(i, l) for i, l in enumerate(net.layers) if l.type == ycfg.CONV and l.size == 3 and (y.layer_kernel(i) or "").startswith("conv_i16_tc2<3>")] if not fp32 else []
+    dom_name = "conv_i16_tc2_kernel<3,14> (persistent tcgen05.mma kind::i8 + TMA-staged activations + exact CUDA-core round-and-saturate; the 3x3 layers with >= 128 output channels)"
     if fp32:
         dom = [(i, l) for i, l in enumerate(net.layers) if l.type == ycfg.CONV and l.size == 3]
         dom_name = "conv_f32_c4_kernel<*,3> (FFMA, all 3x3 conv layers)"
-    elif not dom:   # YOLO2CUDA_TC forced: fall back to "all 3x3 conv layers"
+    elif not dom:   # YOLO2CUDA_TC=0: fall back to "all 3x3 conv layers"
         dom = [(i, l) for i, l in enumerate(net.layers) if l.type == ycfg.CONV and l.size == 3]
         dom_name = "all 3x3 conv layers (YOLO2CUDA_TC=%s)" % os.environ.get("YOLO2CUDA_TC")
     dom_ms = float(sum(lt[i] for i, _ in dom))
@@ -306,6 +304,7 @@ def main():
                 "peak_source": (f"2 x bf16_tflops_sustained of {peak_src} MEASURED_PEAKS.json (int8 dense = 2 x bf16)" if not fp32 else
                                 "nominal fp32 FFMA rate 148 SMs x 128 lanes x 2 FLOP x sm_max_mhz (CUDA-core pipe, 'bound' = fp32 pipe; no measured fp32 peak in MEASURED_PEAKS.json)"),
                 "traffic": None, "launches_per_step": len(dom) * chunks, "avg_launch_ms": dom_ms / len(dom),
+                "algorithmic_bytes_per_launch": None,
                 "share_of_step": dom_ms / all_ms,
                 "exact_steps_per_s": dom_steps * last_chunk / (dom_ms * 1e-3),
                 "exact_steps_per_s_all_conv": conv_steps * last_chunk / (conv_ms * 1e-3),
@@ -316,6 +315,19 @@ def main():
                          "DESIGN.md section 4.  A reference built with Tn=32 runs at ~2.9 k frames/s on the Tn=32 variant of the same "
                          "kernel (profiles/r1_layer_table_int16_b256_tn32.json)") if not fp32 else
                         "fp32 build of the reference (hls/core/core_compute.cpp:121-172): plain FFMA chains on the CUDA cores"}
+    # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of the same command's launches,
+    # captured once under ncu and committed (profiles/r2_tc2_traffic.json, written by profiles/ncu_traffic.py); null when absent
+    # or taken at another pass size.  Algorithmic bytes: input + output tensors of the layer once, plus its weight tiles once.
+    tpath = os.path.join(ROOT, "profiles", "r2_tc2_traffic.json")
+    if not fp32 and dom:
+        alg = sum((l.c * l.h * l.w + l.n * l.out_h * l.out_w) * 2 * last_chunk + l.c * l.n * 9 * 2 for _, l in dom) / len(dom)
+        roofline["algorithmic_bytes_per_launch"] = alg
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("frames_per_pass") == last_chunk and tj.get("kernel_prefix") == "conv_i16_tc2_kernel<3":
+                roofline["traffic"] = tj["dram_bytes_per_launch"]
+                roofline["traffic_source"] = tj.get("source")
     if not fp32:
         fast_tiles, exact_tiles = y.accel.tc_path_counts()
         roofline["tc_fast_path_share"] = fast_tiles / max(1, fast_tiles + exact_tiles)

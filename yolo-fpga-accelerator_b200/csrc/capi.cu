@@ -969,12 +969,13 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                     l.cp = p;
                     // tensor-core path: wide layers only (a CTA covers 128 output channels)
                     l.tc = ctx->use_tc > 0 && e == 2 && so >= 8 && so <= 22 && l.d.n >= ctx->tc_min_ofm;
-                    // auto: the tcgen05 kernel where it measured faster than the CUDA-core kernel (profiles/r2_layer_table_*): every
-                    // 3x3 layer with full 128-channel tiles and >= 64 input channels up to 104 wide, deep 1x1 layers up to 26 wide;
-                    // both paths are bit-exact, so mixing them is safe
-                    if (ctx->use_tc < 0 && e == 2 && so >= 8 && so <= 22 &&
-                        ((l.d.size == 3 && l.d.w <= 104 && l.d.n % 128 == 0 && l.d.c >= 64) ||
-                         (l.d.size == 1 && l.d.w <= 26 && l.d.n >= 256 && l.d.c >= 512)))
+                    // auto: the persistent tcgen05 kernel wherever its 128-channel tiles are at least 80 % full and the chain is deep
+                    // enough to feed it (measured, profiles/r2_layer_table_int16_b128_persistent*.json: 5.1-5.6 T steps/s on every 3x3
+                    // layer from 104 to 13 wide and 4.1-4.6 T on the 1x1 layers, against 2.6-3.8 T on the CUDA cores); the 32- and
+                    // 64-channel layers stay on the CUDA-core kernel.  Both paths are bit-exact, so mixing them is safe.
+                    if (ctx->use_tc < 0 && e == 2 && so >= 8 && so <= 22 && l.d.n * 5 >= ceil_div(l.d.n, 128) * 128 * 4 &&
+                        ((l.d.size == 3 && l.d.c >= 64) || (l.d.size == 1 && l.d.c >= 128)) &&
+                        conv_i16_tc2_eligible(p, l.d.size, net->max_batch))
                         l.tc = true;
                     if (l.tc) {
                         if (!l.w_tc && (rc = net_alloc(net, &l.w_tc, wprep_tc2_bytes(l.d.c, l.d.n, l.d.size)))) return rc;

@@ -123,6 +123,7 @@ namespace y2 {
 size_t wprep_tc2_bytes(int ifm, int ofm, int ksize);
 void launch_wprep_tc2(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, int so, cudaStream_t st);
 int launch_conv_i16_tc2(const ConvFastParams &p, int ksize, cudaStream_t st, const char **variant);
+bool conv_i16_tc2_eligible(const ConvFastParams &p, int ksize, int frames);   // shape / alignment rules of the launcher, without launching
 // tensor-core conv for a reference built with rounding group Tn = 32 (one MMA K slice = one step), csrc/conv_i16_tc32.cu
 size_t wprep_tc32_bytes(int ifm, int ofm, int ksize);
 void launch_wprep_tc32(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, cudaStream_t st);
