@@ -11,6 +11,11 @@
  * linux_app/include/yolo2_config.h:146-151); nothing asserts or aborts.  There is no CPU
  * fallback: without a CUDA device every compute entry returns YOLO2CUDA_INIT_ERROR.
  *
+ * Thread safety: a yolo2cuda_ctx and the networks created from it are single-threaded objects (one host thread at a
+ * time per context); different contexts - e.g. one per GPU - may be used from different threads concurrently.  The
+ * library keeps no mutable process-global state (YOLO2_FPGA itself is not re-entrant: function-local statics,
+ * yolo2_accel.cpp:103-113).
+ *
  * Data contracts shared with the reference:
  *   feature maps   planar [C][H][ceil8(W)], int16 or float   (yolo2_accel.cpp:89-99)
  *   weights        reorganised order produced by yolov2_weight_gen (yolov2_weight_gen.cpp:34-68)

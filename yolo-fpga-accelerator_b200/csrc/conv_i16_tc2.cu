@@ -973,7 +973,7 @@ bool conv_i16_tc2_eligible(const ConvFastParams &cp_in, int ksize, int frames)
     Tc2Params p;
     size_t smem;
     unsigned long long fb;
-    return tc2_plan(cp, ksize, p, smem, fb);
+    return tc2_plan(cp, ksize, p, smem, fb) && tensor_map_encoder() != nullptr;
 }
 
 // Returns 1 when launched, -1 when the shape/shift is not eligible for the tensor-core path, -2 when the tensor map cannot be built.
