@@ -173,6 +173,10 @@ int yolo2cuda_net_get_layer_output(yolo2cuda_net *net, int layer, int frame, voi
 int yolo2cuda_net_region_q(const yolo2cuda_net *net);
 /* Kernels launched by one forward of `batch` frames (0 before the first forward). */
 uint64_t yolo2cuda_net_launches_per_forward(const yolo2cuda_net *net);
+/* Pass schedule of yolo2cuda_net_forward_host / _forward_images_host for batches larger than max_batch: the upload of the first
+ * pass is the only one that does not overlap compute, so such a batch starts with a short RAMP pass of `frames` frames followed by
+ * passes of max_batch (-1 = default max(32, max_batch / 6); 0 = no ramp pass).  The results do not depend on the schedule. */
+int yolo2cuda_net_set_ramp_frames(yolo2cuda_net *net, int frames);
 /* Activation memory.  Default (keep = 0): ONE device arena in which a tensor occupies its bytes only between its first
  * writer and its last reader, so buffers are recycled down the network like the reference's ping-pong scratch arena
  * (yolo2_model.cpp:56-110); the route source (layer 16) and the concat buffer stay alive across the layers between their

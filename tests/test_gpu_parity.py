@@ -729,3 +729,22 @@ def test_compact_detections_records(accel16, oracle):
             want[:, 3:7] = b[f][e[:k]].view(np.uint32)
             want[:, 7] = o[f][e[:k]].view(np.uint32)
             assert np.array_equal(rec[f, :k].view(np.uint32), want)
+
+
+def test_host_forward_pass_schedule_is_invisible(oracle):
+    """yolo2cuda_net_forward_host splits a batch larger than max_batch into a short ramp pass + full passes
+    (yolo2cuda_net_set_ramp_frames); the region tensors must not depend on the schedule."""
+    net, pack = _net_case(416, 416, 3, 8, "default", seed=5)
+    frames = yw.synth_frames(net, 11, seed=77)
+    y = Yolo2Net(net, pack, max_batch=4)
+    try:
+        outs = []
+        for ramp in (-1, 0, 1, 3, 4, 7):
+            y.set_ramp_frames(ramp)
+            outs.append(y.forward(frames).copy())
+        for o in outs[1:]:
+            assert np.array_equal(o.view(np.uint32), outs[0].view(np.uint32))
+        want = oracle.net_forward(net, frames[10], pack)[0]
+        assert np.array_equal(np.ascontiguousarray(outs[0][10]).reshape(-1).view(np.uint32), np.asarray(want, np.float32).reshape(-1).view(np.uint32))
+    finally:
+        y.close()

@@ -467,6 +467,7 @@ struct yolo2cuda_net {
     yolo2cuda_ctx *ctx = nullptr;
     std::vector<LayerPlan> L;
     int max_batch = 0;
+    int ramp_frames = -1;          // first pass of a multi-pass host forward; -1 = max(32, max_batch / 6), 0 = no ramp pass
     int in_c = 0, in_h = 0, in_w = 0;
     size_t region_outputs = 0;
     std::vector<void *> owned;     // device allocations that live as long as the net (weights, staging, scratch)
@@ -1070,12 +1071,25 @@ int yolo2cuda_net_forward_host(yolo2cuda_net *net, const float *frames, int batc
     }
     if (!net->s_h2d) CUDA_OK(ctx, cudaStreamCreateWithFlags(&net->s_h2d, cudaStreamNonBlocking));
     if (!net->s_d2h) CUDA_OK(ctx, cudaStreamCreateWithFlags(&net->s_d2h, cudaStreamNonBlocking));
-    const int npass = (batch + net->max_batch - 1) / net->max_batch;
-    auto pass_frames = [&](int k) { return (k + 1) * net->max_batch <= batch ? net->max_batch : batch - k * net->max_batch; };
+    // Pass schedule.  Only the first pass's upload and the last pass's download are exposed (everything else overlaps a pass's
+    // compute), so a batch of more than one pass starts with a SHORT ramp pass: at 364-frame passes the exposed upload shrinks
+    // from 14 ms to 2 ms per call for ~1 ms of extra tail effect in the ramp pass's kernels.
+    std::vector<int> poff;            // first frame of pass k; poff[npass] = batch
+    {
+        int done = 0;
+        poff.push_back(0);
+        if (batch > net->max_batch) {
+            const int ramp = net->ramp_frames >= 0 ? net->ramp_frames : std::max(32, net->max_batch / 6);
+            if (ramp > 0 && ramp < net->max_batch) { done = ramp; poff.push_back(done); }
+        }
+        while (done < batch) { done = std::min(batch, done + net->max_batch); poff.push_back(done); }
+    }
+    const int npass = (int)poff.size() - 1;
+    auto pass_frames = [&](int k) { return poff[k + 1] - poff[k]; };
     auto issue_h2d = [&](int k) -> int {
         const int buf = k & 1;
         if (k >= 2) CUDA_OK(ctx, cudaStreamWaitEvent(net->s_h2d, net->ev_comp[buf], 0));   // pass k-2 has consumed this buffer
-        CUDA_OK(ctx, cudaMemcpyAsync(net->d_frames2[buf], frames + (size_t)k * net->max_batch * frame_elems,
+        CUDA_OK(ctx, cudaMemcpyAsync(net->d_frames2[buf], frames + (size_t)poff[k] * frame_elems,
                                      frame_elems * pass_frames(k) * sizeof(float), cudaMemcpyHostToDevice, net->s_h2d));
         CUDA_OK(ctx, cudaEventRecord(net->ev_h2d[buf], net->s_h2d));
         return YOLO2CUDA_SUCCESS;
@@ -1092,7 +1106,7 @@ int yolo2cuda_net_forward_host(yolo2cuda_net *net, const float *frames, int batc
         if ((rc = forward_chunk(net, (const float *)net->d_frames2[buf], B, (float *)net->d_region2[buf]))) return rc;
         CUDA_OK(ctx, cudaEventRecord(net->ev_comp[buf], st));
         CUDA_OK(ctx, cudaStreamWaitEvent(net->s_d2h, net->ev_comp[buf], 0));
-        CUDA_OK(ctx, cudaMemcpyAsync(region_out + (size_t)k * net->max_batch * net->region_outputs, net->d_region2[buf],
+        CUDA_OK(ctx, cudaMemcpyAsync(region_out + (size_t)poff[k] * net->region_outputs, net->d_region2[buf],
                                      net->region_outputs * B * sizeof(float), cudaMemcpyDeviceToHost, net->s_d2h));
         CUDA_OK(ctx, cudaEventRecord(net->ev_d2h[buf], net->s_d2h));
     }
@@ -1170,6 +1184,13 @@ int yolo2cuda_net_get_layer_output(yolo2cuda_net *net, int layer, int frame, voi
 
 int yolo2cuda_net_region_q(const yolo2cuda_net *net) { return net ? net->region_q : 0; }
 uint64_t yolo2cuda_net_launches_per_forward(const yolo2cuda_net *net) { return net ? net->launches_per_forward : 0; }
+int yolo2cuda_net_set_ramp_frames(yolo2cuda_net *net, int frames)
+{
+    if (!net || frames < -1) return YOLO2CUDA_ERROR;
+    net->ramp_frames = frames;
+    return YOLO2CUDA_SUCCESS;
+}
+
 int yolo2cuda_net_set_debug_keep(yolo2cuda_net *net, int keep)
 {
     if (!net) return YOLO2CUDA_ERROR;

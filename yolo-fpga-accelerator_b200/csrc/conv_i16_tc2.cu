@@ -76,8 +76,12 @@ constexpr int kBuilders = 3;        // next warpgroup: builder bw takes the tile
 constexpr int kIssuer = kEpiWarps + 4;   // last warpgroup: issuer iw takes the tiles r = iw (mod 4).  One warp issues one MMA per ~29 cycles
 constexpr int kIssuers = 4;         //   (profiles/microbench/umma_issue.cu) and pays ~100 cycles per mbarrier wait
 constexpr int kThreads = (kEpiWarps + 8) * 32;   // 768 threads, 80 registers at launch; setmaxnreg then moves registers
-constexpr int kEpiRegs = 96;        //   from the helper warps (48) to the epilogue warps (96)
-constexpr int kHelperRegs = 48;
+#ifndef Y2_TC2_EPI_REGS
+#define Y2_TC2_EPI_REGS 96
+#define Y2_TC2_HELPER_REGS 48
+#endif
+constexpr int kEpiRegs = Y2_TC2_EPI_REGS;        //   from the helper warps (48) to the epilogue warps (96)
+constexpr int kHelperRegs = Y2_TC2_HELPER_REGS;
 static_assert(kBRing == kR && kR % kIssuers == 0 && kR % kGroups == 0 && (kR / 2) % kBuilders == 0, "ring = one K-block; see go[]");
 constexpr int kWBytes = kM * 64;    // one K-block of weights: [row][hi 32 B | lo 32 B], 16-byte chunks XOR-swizzled by (row>>1)&3
 constexpr int kBBytes = kN * 32;    // one plane of one activation tile

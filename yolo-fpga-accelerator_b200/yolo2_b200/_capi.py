@@ -61,6 +61,7 @@ SYMBOLS = {
     "yolo2cuda_net_region_q": (C.c_int, [C.c_void_p]),
     "yolo2cuda_net_launches_per_forward": (C.c_uint64, [C.c_void_p]),
     "yolo2cuda_net_set_debug_keep": (C.c_int, [C.c_void_p, C.c_int]),
+    "yolo2cuda_net_set_ramp_frames": (C.c_int, [C.c_void_p, C.c_int]),
     "yolo2cuda_net_activation_bytes": (C.c_size_t, [C.c_void_p]),
     "yolo2cuda_net_layer_times": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "yolo2cuda_net_layer_kernel": (C.c_char_p, [C.c_void_p, C.c_int]),

@@ -43,6 +43,10 @@ class Yolo2Net:
                                                  vp(aq), len(aq) if aq is not None else 0)
         _capi.check(self.accel.ctx, rc)
 
+    def set_ramp_frames(self, frames: int):
+        """first (short) pass of a multi-pass host forward: yolo2cuda_net_set_ramp_frames (-1 default, 0 none)"""
+        _capi.check(self.accel.ctx, self.lib.yolo2cuda_net_set_ramp_frames(self.handle, int(frames)))
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.yolo2cuda_net_destroy(self.handle)
@@ -211,25 +215,41 @@ def yolov2_cuda_ps(net: _cfg.Network, input: np.ndarray, pack: WeightsPack, devi
         y.close()
 
 
-def best_pass_size(net: _cfg.Network, lo: int = 128, hi: int = 400, sms: int = 148, ctas_per_sm: int = 2) -> int:
-    """Frames per device pass that fills the conv grids' last wave best.
+def _on_tensor_cores(l) -> bool:
+    """csrc/capi.cu auto policy: 128-channel tiles at least 80 % full and a deep enough chain"""
+    return l.n * 5 >= -(-l.n // 128) * 128 * 4 and ((l.size == 3 and l.c >= 64) or (l.size == 1 and l.c >= 128))
 
-    A conv launch has ceil(pass*H / (64 // (W/13))) bands x ceil(OFM/16) CTAs of equal cost (csrc/conv_i16.cu)
-    and sms*ctas_per_sm CTAs run at a time, so the pass size decides how full the last wave of each layer
-    is.  Returns the size in [lo, hi] maximising the step-weighted average of waves/ceil(waves)."""
+
+def pass_efficiency(net: _cfg.Network, n: int, sms: int = 148) -> float:
+    """Step-weighted fill of the last round / wave of every conv launch for a pass of n frames.
+
+    The persistent tcgen05 kernel (csrc/conv_i16_tc2.cu) walks ceil(n*H*W/48) * ceil(OFM/128) equal work items on `sms` CTAs;
+    the CUDA-core kernel (csrc/conv_i16.cu) launches ceil(n*H / (64 // (W/13))) bands x ceil(OFM/16) CTAs, two per SM."""
     import math
-    convs = [l for l in net.layers if l.type == _cfg.CONV]
-    slots = sms * ctas_per_sm
-
-    def eff(n):
-        ideal = real = 0.0
-        for l in convs:
+    ideal = real = 0.0
+    for l in net.layers:
+        if l.type != _cfg.CONV:
+            continue
+        steps = math.ceil(l.c / 4) * l.size * l.size
+        if _on_tensor_cores(l):
+            units, slots, cost = math.ceil(n * l.h * l.w / 48) * math.ceil(l.n / 128), sms, steps * 48 * 128
+        else:
             tp = 13 if l.w % 13 == 0 else 7
             sw = -(-l.w // tp)
             rb = max(1, 64 // sw)
-            ctas = math.ceil(n * l.h / rb) * math.ceil(l.n / 16)
-            cost = math.ceil(l.c / 4) * l.size * l.size
-            ideal += ctas / slots * cost
-            real += math.ceil(ctas / slots) * cost
-        return ideal / real
-    return max(range(lo, hi + 1), key=lambda n: (round(eff(n), 4), -n))
+            units, slots, cost = math.ceil(n * l.h / rb) * math.ceil(l.n / 16), 2 * sms, steps * rb * l.w * 16 * 1.6
+        ideal += units / slots * cost
+        real += math.ceil(units / slots) * cost
+    return ideal / real
+
+
+def best_pass_size(net: _cfg.Network, lo: int = 128, hi: int = 400, sms: int = 148) -> int:
+    """Frames per device pass in [lo, hi] with the best pass_efficiency (the largest among equals).  For YOLOv2-416 on 148 SMs
+    these are the multiples of 21 frames: 21 * 169 pixels = 74 tiles of 48, x 8 channel tiles = 4 * 148 items."""
+    return max(range(lo, hi + 1), key=lambda n: (round(pass_efficiency(net, n, sms), 2), n))
+
+
+def best_ramp_size(net: _cfg.Network, max_batch: int, sms: int = 148) -> int:
+    """First (short) pass of a multi-pass host forward: the best-filling size between 32 frames and a quarter of a pass."""
+    hi = max(33, max_batch // 4)
+    return max(range(32, hi + 1), key=lambda n: (round(pass_efficiency(net, n, sms), 2), -n))
