@@ -328,8 +328,9 @@ def main():
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            if tj.get("frames_per_pass") == last_chunk and tj.get("kernel_prefix") == "conv_i16_tc2_kernel<3":
-                roofline["traffic"] = tj["dram_bytes_per_launch"]
+            if tj.get("frames_per_step") == B and tj.get("kernel_prefix") == "conv_i16_tc2_kernel<3":
+                # the capture averages over the launches of every pass of a step; scale to the pass the times above refer to
+                roofline["traffic"] = tj["dram_bytes_per_launch"] * last_chunk * chunks / B
                 roofline["traffic_source"] = tj.get("source")
     if not fp32:
         fast_tiles, exact_tiles = y.accel.tc_path_counts()

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Per-kernel totals from an ncu --csv launch list taken with
    --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
-Usage: python profiles/ncu_traffic.py launches.csv frames_per_pass [out.json]
+Usage: python profiles/ncu_traffic.py launches.csv frames_per_step [out.json]
 Prints one row per kernel name (launches, total ms, share of device time, DRAM GB per launch, achieved DRAM GB/s) and writes
 the per-launch DRAM traffic of the dominant kernel (conv_i16_tc2_kernel<3, .>) for bench.py's roofline.traffic."""
 import csv
@@ -30,7 +30,7 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 dom = [(k, a) for k, a in agg.items() if re.match(r"conv_i16_tc2_kernel<3", k)]
 if dom and len(sys.argv) > 3:
     n = sum(a[0] for _, a in dom)
-    out = {"kernel_prefix": "conv_i16_tc2_kernel<3", "frames_per_pass": int(sys.argv[2]), "launches": n,
+    out = {"kernel_prefix": "conv_i16_tc2_kernel<3", "frames_per_step": int(sys.argv[2]), "launches": n,
            "dram_bytes_per_launch": sum(a[2] for _, a in dom) / n, "ms_per_launch_under_ncu": sum(a[1] for _, a in dom) / n,
            "share_of_device_time_under_ncu": sum(a[1] for _, a in dom) / tot,
            "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over "

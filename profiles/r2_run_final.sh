@@ -8,4 +8,4 @@ YOLO2CUDA_LIB=$V/libyolo2cuda_grid3.so timeout 900 python -m pytest tests/test_g
 timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/f_tests.log 2>&1; echo "tests rc $?"; tail -3 gpurun_out/f_tests.log
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/f_bench.json 2> gpurun_out/f_bench.err; echo "bench rc $?"; cut -c1-300 gpurun_out/f_bench.json
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_bench_launches_ncu.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/ncu_bench.log 2>&1; echo "ncu list rc $?"
-python profiles/ncu_traffic.py gpurun_out/r2_bench_launches_ncu.csv 364 gpurun_out/r2_tc2_traffic.json | head -12
+python profiles/ncu_traffic.py gpurun_out/r2_bench_launches_ncu.csv 735 gpurun_out/r2_tc2_traffic.json
