@@ -972,10 +972,12 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                     l.tc = ctx->use_tc > 0 && e == 2 && so >= 8 && so <= 22 && l.d.n >= ctx->tc_min_ofm;
                     // auto: the persistent tcgen05 kernel wherever its 128-channel tiles are at least 80 % full and the chain is deep
                     // enough to feed it (measured, profiles/r2_layer_table_int16_b128_persistent*.json: 5.1-5.6 T steps/s on every 3x3
-                    // layer from 104 to 13 wide and 4.1-4.6 T on the 1x1 layers, against 2.6-3.8 T on the CUDA cores); the 32- and
-                    // 64-channel layers stay on the CUDA-core kernel.  Both paths are bit-exact, so mixing them is safe.
-                    if (ctx->use_tc < 0 && e == 2 && so >= 8 && so <= 22 && l.d.n * 5 >= ceil_div(l.d.n, 128) * 128 * 4 &&
-                        ((l.d.size == 3 && l.d.c >= 64) || (l.d.size == 1 && l.d.c >= 128)) &&
+                    // layer from 104 to 13 wide and 4.1-4.6 T on the 1x1 layers, against 2.6-3.8 T on the CUDA cores); layer 0 (3 input
+                    // channels, 32 output channels) stays on the CUDA-core kernel.  Both paths are bit-exact, so mixing them is safe.
+                    // (128-channel tiles, or 64-channel tiles x two pixel sets when those fill better: conv_i16_tc2.cu half_mode)
+                    const bool fill128 = l.d.n * 5 >= ceil_div(l.d.n, 128) * 128 * 4, fill64 = l.d.n * 5 >= ceil_div(l.d.n, 64) * 64 * 4;
+                    if (ctx->use_tc < 0 && e == 2 && so >= 8 && so <= 22 && (fill128 || fill64) &&
+                        ((l.d.size == 3 && l.d.c >= 32) || (l.d.size == 1 && l.d.c >= 128)) &&
                         conv_i16_tc2_eligible(p, l.d.size, net->max_batch))
                         l.tc = true;
                     if (l.tc) {

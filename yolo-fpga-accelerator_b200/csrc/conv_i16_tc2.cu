@@ -267,9 +267,9 @@ __device__ __forceinline__ unsigned long long smem_desc(const void *p)
     d |= 1ull << 46;  // descriptor version for sm_100
     return d;
 }
-__host__ __device__ constexpr unsigned idesc_i8(int a_signed, int b_signed)
+__host__ __device__ constexpr unsigned idesc_i8(int a_signed, int b_signed, unsigned m_rows = kM)
 {
-    return (2u << 4) | ((unsigned)a_signed << 7) | ((unsigned)b_signed << 10) | ((unsigned)(kN >> 3) << 17) | ((unsigned)(kM >> 4) << 24);
+    return (2u << 4) | ((unsigned)a_signed << 7) | ((unsigned)b_signed << 10) | ((unsigned)(kN >> 3) << 17) | ((m_rows >> 4) << 24);
 }
 __host__ __device__ inline int operand_off(int row, int k) { return (((row >> 3) * 2 + (k >> 4)) * 8 + (row & 7)) * 16 + (k & 15); }
 
@@ -320,7 +320,18 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, 
 constexpr int kProducer = kEpiWarps + kBuilders;   // the fourth warp of the builder warpgroup: TMA producer of the activation runs
 constexpr int kTabSlots = 4;                        // per-item tables live in a ring: the producer runs at most two items ahead of the epilogue
 constexpr int kNumBars = 2 * kWRing + 4 + 3 * kBRing + 4;
-constexpr int kFixedBytes = ((kWRing * kWBytes + kBRing * 2 * kBBytes + kNumBars * 8 + 16 + kTabSlots * kPT * (16 + 8)) + 127) & ~127;
+// HALF mode (64 output channels per item): the 128 TMEM lanes hold 64 channels x TWO pixel sets.  A tcgen05.mma with M = 64 puts
+// row r in lane (r/16)*32 + r%16, and its D (and TMEM A) address may carry a lane offset of 16 (profiles/microbench/umma_m64_layout.cu,
+// profiles/r2_umma_m64_layout.jsonl), so two M = 64 products - same weights, the activation tiles of pixel set 0 / set 1 - fill all
+// 128 lanes and every epilogue warp works with 32 live lanes.  An item is then 96 consecutive pixels x 64 channels; the 64-channel
+// layers (32->64 3x3 @208, 128->64 and 512->64 1x1) would otherwise run half-empty 128-row tiles or stay on the CUDA cores.
+template <bool HALF> struct Tc2Shape {
+    static constexpr int kSets = HALF ? 2 : 1;              // pixel sets per item
+    static constexpr int kPTI = kPT * kSets;                // pixels per item
+    static constexpr int kRows = HALF ? 64 : 128;           // output channels per item
+    static constexpr int kSlotBytes = kSets * 2 * kBBytes;  // one ring slot: [set][hi 1 KB | lo 1 KB]
+    static constexpr int kFixedBytes = ((kWRing * kWBytes + kBRing * kSlotBytes + kNumBars * 8 + 16 + kTabSlots * kPTI * (16 + 8)) + 127) & ~127;
+};
 
 // PERSISTENT kernel (round 2): one CTA per SM walks the work items  item = blockIdx.x + n * gridDim.x  (static round-robin;
 // item = (48-pixel tile, 128-channel tile)).  Tensor memory, the barriers, the operand ring and the rounding row are set up once;
@@ -336,17 +347,19 @@ constexpr int kFixedBytes = ((kWRing * kWBytes + kBRing * 2 * kBBytes + kNumBars
 // way, and coordinates outside the tensor are zero-filled by the TMA unit.  An item that straddles a frame boundary stages a
 // second run for the next frame.  (A 4-D [frame][G][H][W] map with per-row boxes is not legal for the 13- and 19-wide layers:
 // their 104- / 152-byte rows break the 16-byte global-stride rule, SURVEY.md appendix A.)
-template <int KS, int SO>
+template <int KS, int SO, bool HALF>
 __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int K2 = KS * KS;
     constexpr int PAD = KS / 2;
     constexpr bool kFast = SO <= 16;   // 65536 * HH is a multiple of 2^so: HH enters the chain linearly
     constexpr bool kLd32 = SO <= 14 && Y2_TC2_LD32 != 0;   // (so = 15 spills with it)
+    using Sh = Tc2Shape<HALF>;
+    constexpr int kSets = Sh::kSets, kPTI = Sh::kPTI, kSlotBytes = Sh::kSlotBytes, kFixedBytes = Sh::kFixedBytes;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sW = smem;                                    // kWRing x 8 KB
     unsigned char *sB = sW + kWRing * kWBytes;                   // kBRing x (hi 1 KB | lo 1 KB); a builder pair = two consecutive slots
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sB + kBRing * 2 * kBBytes);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sB + kBRing * kSlotBytes);
     unsigned long long *w_full = bars, *w_empty = w_full + kWRing, *a_full = w_empty + kWRing, *a_empty = a_full + 2,
                        *go = a_empty + 2, *mma_done = go + kBRing, *rd_done = mma_done + kBRing, *x_full = rd_done + kBRing,
                        *x_empty = x_full + 2;
@@ -363,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
     int *s_amax = reinterpret_cast<int *>(tmem_slot + 1);        // largest |output| of this CTA
     unsigned *s_cnt = tmem_slot + 2;                             // [2]: warp-tiles through the fast / the exact path
     int4 *pxinfo = reinterpret_cast<int4 *>(tmem_slot + 4);      // [slot][48]: (run index of tap (0,0) for even / odd channel groups, tap-row mask | tap-column mask << 3, -)
-    long long *outoff = reinterpret_cast<long long *>(pxinfo + kTabSlots * kPT);   // [slot][48]: output element offset of the pixel's group-0 word, -1 = no such pixel
+    long long *outoff = reinterpret_cast<long long *>(pxinfo + kTabSlots * kPTI);   // [slot][48]: output element offset of the pixel's group-0 word, -1 = no such pixel
     uint2 *sX = reinterpret_cast<uint2 *>(smem + kFixedBytes);   // 2 chunks x GS groups x 2 segments x seg_px pixels
 
     // the warp index through a shuffle: the compiler then knows it (and every TMEM address / role branch derived from it) is warp-uniform
@@ -387,14 +400,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = tid; i < kBRing * 2 * kBBytes / 4; i += kThreads) reinterpret_cast<unsigned *>(sB)[i] = 0u;
+    for (int i = tid; i < kBRing * kSlotBytes / 4; i += kThreads) reinterpret_cast<unsigned *>(sB)[i] = 0u;
     __syncthreads();
     {   // rounding row (k = 28) of every lo-plane activation tile: b = 2^min(7, e) where a*b = 2^e is the constant to inject
         const int e = (SO <= 15) ? SO - 1 : SO - 9;   // `half` into LL, or half/256 into M
         const int eb = e < 7 ? e : 7;
-        for (int i = tid; i < kBRing * kN; i += kThreads) {
-            int slot = i / kN, n = i - slot * kN;
-            sB[(slot * 2 + 1) * kBBytes + operand_off(n, 28)] = (unsigned char)(1u << eb);
+        for (int i = tid; i < kBRing * kSets * kN; i += kThreads) {      // tile = (ring slot, pixel set); its lo plane is the second KB
+            int tile = i / kN, n = i - tile * kN;
+            sB[(tile * 2 + 1) * kBBytes + operand_off(n, 28)] = (unsigned char)(1u << eb);
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -411,7 +424,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             // one elected lane issues.  Per tile ONE barrier (go[r]) gates the issue. =====
             const int iw = warp - kIssuer;
             const unsigned long long dB0 = smem_desc(sB);
-            constexpr unsigned long long kBStep = (2 * kBBytes) >> 4, kBPlane = kBBytes >> 4;   // descriptor address units (16 B)
+            constexpr unsigned long long kBStep = kSlotBytes >> 4, kBPlane = kBBytes >> 4;   // descriptor address units (16 B)
+            constexpr unsigned kMma = HALF ? 64u : 128u;
             unsigned elected;
             asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
             // weights of global K-block gbn (item gbn / nkb of this CTA, K-block gbn % nkb of that item's channel tile)
@@ -470,12 +484,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                     PROF_TL(b * kR + r, 2);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     if (elected) {
-                        const unsigned long long dBh = dB0 + r * kBStep, dBl = dBh + kBPlane;
-                        const unsigned d0 = tmem + tb * kBufCols;
-                        umma_i8_ts(d0 + kPlaneCols, ah, dBl, idesc_i8(1, 0), 0);       // M  = hi*lo
-                        umma_i8_ts(d0 + kPlaneCols, al, dBh, idesc_i8(0, 1), 1);       //    + lo*hi
-                        umma_i8_ts(d0 + 2 * kPlaneCols, al, dBl, idesc_i8(0, 0), 0);   // LL (+ the rounding constant through K row 28)
-                        umma_i8_ts(d0, ah, dBh, idesc_i8(1, 1), 0);                    // HH per step in columns 0..27, sum over the K-block's steps in 28..31
+#pragma unroll
+                        for (int st = 0; st < kSets; ++st) {        // HALF: pixel set st -> lanes 16*st .. 16*st+15 of every quadrant
+                            const unsigned long long dBh = dB0 + r * kBStep + st * (2 * kBPlane), dBl = dBh + kBPlane;
+                            const unsigned lo16 = (unsigned)(16 * st) << 16;
+                            const unsigned d0 = tmem + tb * kBufCols + lo16, ahs = ah + lo16, als = al + lo16;
+                            umma_i8_ts(d0 + kPlaneCols, ahs, dBl, idesc_i8(1, 0, kMma), 0);       // M  = hi*lo
+                            umma_i8_ts(d0 + kPlaneCols, als, dBh, idesc_i8(0, 1, kMma), 1);       //    + lo*hi
+                            umma_i8_ts(d0 + 2 * kPlaneCols, als, dBl, idesc_i8(0, 0, kMma), 0);   // LL (+ the rounding constant through K row 28)
+                            umma_i8_ts(d0, ahs, dBh, idesc_i8(1, 1, kMma), 0);                    // HH per step in columns 0..27, sum over the K-block's steps in 28..31
+                        }
                         umma_commit(&mma_done[r]);                             // epilogue (tile ready) waits on it
                         if (j == kR / kIssuers - 1) umma_commit(&a_empty[b & 1]);   // this warp's reads of the weight slot are done
                     }
@@ -495,11 +513,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             for (int n = 0; n < nloc; ++n) {
                 const int item = (int)blockIdx.x + n * (int)gridDim.x;
                 const int pt = item / p.mtiles;
-                const long long pix0 = (long long)pt * kPT;
+                const long long pix0 = (long long)pt * kPTI;
                 const int f0 = (int)(pix0 / p.HW);
                 const int pin0 = (int)(pix0 - (long long)f0 * p.HW);
-                const int qsplit = min(kPT, p.HW - pin0);    // pixels q >= qsplit lie in frame f0 + 1
-                const int nseg = (qsplit < kPT && f0 + 1 < p.B) ? 2 : 1;
+                const int qsplit = min(kPTI, p.HW - pin0);   // pixels q >= qsplit lie in frame f0 + 1
+                const int nseg = (qsplit < kPTI && f0 + 1 < p.B) ? 2 : 1;
                 for (int c = 0; c < p.nchunks; ++c, ++gc) {
                     const int buf = gc & 1;
                     if (gc >= 2) mbar_wait(&x_empty[buf], ((gc >> 1) - 1) & 1);   // the builders have left the chunk that used this buffer
@@ -507,9 +525,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                         // Tables of item n (ring slot n & 3), written AFTER the wait above: the builders have then finished item n-2 at least,
                         // so every epilogue warp has read a tile of item n-3 and is done with the tables of item n-4 (its output store).
                         // The builders / epilogue warps see them through the x_full -> go -> mma_done barrier chain.
-                        int4 *pi = pxinfo + (n & (kTabSlots - 1)) * kPT;
-                        long long *oo = outoff + (n & (kTabSlots - 1)) * kPT;
-                        for (int q = lane; q < kPT; q += 32) {
+                        int4 *pi = pxinfo + (n & (kTabSlots - 1)) * kPTI;
+                        long long *oo = outoff + (n & (kTabSlots - 1)) * kPTI;
+                        for (int q = lane; q < kPTI; q += 32) {
                             const int seg = q >= qsplit;
                             const int f = f0 + seg;
                             const int pin = seg ? q - qsplit : pin0 + q;
@@ -560,7 +578,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             int gb = 0;                                 // global K-block counter of this CTA
             PROF_DECL
             for (int n = 0; n < nloc; ++n) {
-                const int4 *pi = pxinfo + (n & (kTabSlots - 1)) * kPT;
+                const int4 *pi = pxinfo + (n & (kTabSlots - 1)) * kPTI;
                 const int gc0 = n * p.nchunks;
                 for (int b = 0; b < p.nkb; ++b, ++gb) {
                     PROF_ADD(4);
@@ -596,27 +614,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                         }
                         PROF_ADD(1);
                         PROF_TL(gb * kR + 2 * j, 0); PROF_TL(gb * kR + 2 * j + 1, 0);
-                        unsigned char *bh = sB + (j * 4) * kBBytes;
                         if (has) {
-                            unsigned hi0 = 0, lo0 = 0, hi1 = 0, lo1 = 0;
-                            const int4 ia = pi[2 * j * kPx + p0], ib = pi[(2 * j + 1) * kPx + p0];
-                            if ((ia.z & need) == need) {
-                                const uint2 xa = xs0[godd ? ia.y : ia.x];
-                                hi0 = __byte_perm(xa.x, xa.y, 0x7531);
-                                lo0 = __byte_perm(xa.x, xa.y, 0x6420);
-                            }
-                            if ((ib.z & need) == need) {
-                                const uint2 xb = xs0[godd ? ib.y : ib.x];
-                                hi1 = __byte_perm(xb.x, xb.y, 0x7531);
-                                lo1 = __byte_perm(xb.x, xb.y, 0x6420);
-                            }
-                            *reinterpret_cast<unsigned *>(bh + off0) = hi0;
-                            *reinterpret_cast<unsigned *>(bh + kBBytes + off0) = lo0;
-                            *reinterpret_cast<unsigned *>(bh + 2 * kBBytes + off0) = hi1;
-                            *reinterpret_cast<unsigned *>(bh + 3 * kBBytes + off0) = lo1;
-                            if constexpr (kFast) {
-                                *reinterpret_cast<unsigned *>(bh + offd) = hi0;
-                                *reinterpret_cast<unsigned *>(bh + 2 * kBBytes + offd) = hi1;
+#pragma unroll
+                            for (int st = 0; st < kSets; ++st) {    // pixel set st of the item: pixels st*48 + tile*4 + p0
+                                unsigned char *bh0 = sB + (2 * j) * kSlotBytes + st * 2 * kBBytes, *bh1 = bh0 + kSlotBytes;
+                                unsigned hi0 = 0, lo0 = 0, hi1 = 0, lo1 = 0;
+                                const int4 ia = pi[st * kPT + 2 * j * kPx + p0], ib = pi[st * kPT + (2 * j + 1) * kPx + p0];
+                                if ((ia.z & need) == need) {
+                                    const uint2 xa = xs0[godd ? ia.y : ia.x];
+                                    hi0 = __byte_perm(xa.x, xa.y, 0x7531);
+                                    lo0 = __byte_perm(xa.x, xa.y, 0x6420);
+                                }
+                                if ((ib.z & need) == need) {
+                                    const uint2 xb = xs0[godd ? ib.y : ib.x];
+                                    hi1 = __byte_perm(xb.x, xb.y, 0x7531);
+                                    lo1 = __byte_perm(xb.x, xb.y, 0x6420);
+                                }
+                                *reinterpret_cast<unsigned *>(bh0 + off0) = hi0;
+                                *reinterpret_cast<unsigned *>(bh0 + kBBytes + off0) = lo0;
+                                *reinterpret_cast<unsigned *>(bh1 + off0) = hi1;
+                                *reinterpret_cast<unsigned *>(bh1 + kBBytes + off0) = lo1;
+                                if constexpr (kFast) {
+                                    *reinterpret_cast<unsigned *>(bh0 + offd) = hi0;
+                                    *reinterpret_cast<unsigned *>(bh1 + offd) = hi1;
+                                }
                             }
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -656,11 +677,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
         int mt = (int)blockIdx.x % p.mtiles;        // channel tile of the current item
         // loaded one item / one K-block ahead: a global load's latency (hundreds of cycles) must never sit between a tile becoming
         // ready and its read-out
-        int bias_next = (mt * kM + row < p.OFM) ? (int)p.bias[mt * kM + row] : 0;
+        // HALF: lane L of quadrant q4 is channel 16*q4 + L%16 of pixel set L/16 (the weight tiles / norm tables are stored per LANE)
+        const int crow = HALF ? 16 * q4 + (lane & 15) : row, pset = HALF ? lane >> 4 : 0;
+        constexpr int kRows = Sh::kRows;
+        int bias_next = (mt * kRows + crow < p.OFM) ? (int)p.bias[mt * kRows + crow] : 0;
         const unsigned *wn = p.wnorm + (size_t)mt * p.nkb * kM + row;
         unsigned w1_next = wn[0];
         for (int n = 0; n < nloc; ++n) {
-            const int m = mt * kM + row;
+            const int m = mt * kRows + crow;
             {
                 const long long base = round_shift64((long long)bias_next, p.sb);
                 const long long rb = (1LL << (33 - SO)) + 2;      // |(P + half) >> so| <= 2^(33-so): clamping the bias term there cannot change clamp16(bias + r)
@@ -674,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                 }
             }
             const int mt_next = (n + 1 < nloc) ? ((int)blockIdx.x + (n + 1) * (int)gridDim.x) % p.mtiles : mt;
-            if (n + 1 < nloc) bias_next = (mt_next * kM + row < p.OFM) ? (int)p.bias[mt_next * kM + row] : 0;
+            if (n + 1 < nloc) bias_next = (mt_next * kRows + crow < p.OFM) ? (int)p.bias[mt_next * kRows + crow] : 0;
             const unsigned *wn_next = p.wnorm + (size_t)mt_next * p.nkb * kM + row;
             for (int b = 0; b < p.nkb; ++b, ++gb) {
                 PROF_ADD(4);
@@ -779,7 +803,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             }
             // ---- the item's 12 pixels of this thread's channel: leaky, store, largest |output| ----
             if (m < p.OFM) {
-                const long long *oo = outoff + (n & (kTabSlots - 1)) * kPT;
+                const long long *oo = outoff + (n & (kTabSlots - 1)) * kPTI + pset * kPT;
                 int16_t *om = p.out + ((long long)(m >> 2) * p.HW * 4 + (m & 3));
 #pragma unroll
                 for (int rr = 0; rr < kTPG; ++rr) {
@@ -824,7 +848,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
 // Output: [mtile][kblock][row 0..127][hi plane 32 B | lo plane 32 B], the four 16-byte chunks of a row stored at
 // chunk ^ ((row>>1)&3) (conflict-free LDS.128 by 32 consecutive rows); K byte 28 = the rounding constant's weight-side factor.
 __global__ void wprep_tc2_kernel(const int16_t *__restrict__ blob, unsigned char *__restrict__ dst, int ifm, int ofm, int ksize,
-                                 int TM, int TN, int nkb, int so, long long total)
+                                 int TM, int TN, int nkb, int so, long long total, int half)
 {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -834,7 +858,7 @@ __global__ void wprep_tc2_kernel(const int16_t *__restrict__ blob, unsigned char
     int ml = r % kM; r /= kM;
     int b = r % nkb;
     int mtile = r / nkb;
-    int m = mtile * kM + ml;
+    int m = half ? mtile * 64 + 16 * (ml >> 5) + (ml & 15) : mtile * kM + ml;    // HALF: tile row = TMEM lane, both pixel-set halves hold the channel
     int hi = 0, lo = 0;
     if (k < 28) {
         int sigma = b * kSteps + (k >> 2), t = k & 3;
@@ -860,7 +884,7 @@ __global__ void wprep_tc2_kernel(const int16_t *__restrict__ blob, unsigned char
 
 // Fast-path bound table: [mtile][kblock][row] = sum of |w| over the (up to) 28 weights of the row's K-block.
 __global__ void wnorm_tc2_kernel(const int16_t *__restrict__ blob, unsigned *__restrict__ dst, int ifm, int ofm, int ksize, int TM, int TN,
-                                 int nkb, long long total)
+                                 int nkb, long long total, int half)
 {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -868,7 +892,7 @@ __global__ void wnorm_tc2_kernel(const int16_t *__restrict__ blob, unsigned *__r
     const int ml = idx % kM;
     long long r = idx / kM;
     const int b = r % nkb, mtile = r / nkb;
-    const int m = mtile * kM + ml;
+    const int m = half ? mtile * 64 + 16 * (ml >> 5) + (ml & 15) : mtile * kM + ml;
     unsigned sum = 0;
     if (m < ofm)
         for (int k = 0; k < 28; ++k) {
@@ -881,20 +905,20 @@ __global__ void wnorm_tc2_kernel(const int16_t *__restrict__ blob, unsigned *__r
     dst[idx] = sum;
 }
 
-template <int KS, int SO>
+template <int KS, int SO, bool HALF>
 void launch_one(const Tc2Params &p, const CUtensorMap &tmap, dim3 grid, size_t smem, cudaStream_t st)
 {
     // set on every launch (a microsecond): the attribute is per device and a host may drive several GPUs from several threads,
     // so a cached "already configured" flag would be a data race for nothing
-    cudaFuncSetAttribute(conv_i16_tc2_kernel<KS, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    conv_i16_tc2_kernel<KS, SO><<<grid, kThreads, smem, st>>>(p, tmap);
+    cudaFuncSetAttribute(conv_i16_tc2_kernel<KS, SO, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    conv_i16_tc2_kernel<KS, SO, HALF><<<grid, kThreads, smem, st>>>(p, tmap);
 }
 
-template <int KS>
+template <int KS, bool HALF>
 bool dispatch_so(const Tc2Params &p, const CUtensorMap &tmap, int so, dim3 grid, size_t smem, cudaStream_t st)
 {
     switch (so) {
-#define Y2_TC2_CASE(S) case S: launch_one<KS, S>(p, tmap, grid, smem, st); return true;
+#define Y2_TC2_CASE(S) case S: launch_one<KS, S, HALF>(p, tmap, grid, smem, st); return true;
         Y2_TC2_CASE(8) Y2_TC2_CASE(9) Y2_TC2_CASE(10) Y2_TC2_CASE(11) Y2_TC2_CASE(12) Y2_TC2_CASE(13) Y2_TC2_CASE(14) Y2_TC2_CASE(15)
         Y2_TC2_CASE(16) Y2_TC2_CASE(17) Y2_TC2_CASE(18) Y2_TC2_CASE(19) Y2_TC2_CASE(20) Y2_TC2_CASE(21) Y2_TC2_CASE(22)
 #undef Y2_TC2_CASE
@@ -902,10 +926,19 @@ bool dispatch_so(const Tc2Params &p, const CUtensorMap &tmap, int so, dim3 grid,
     }
 }
 
+// HALF mode (64 channels x two pixel sets per item) when the 128-row tiles would be less than 80 % full and 64-row tiles fill better
+bool half_mode(int ofm)
+{
+    const int full128 = ceil_div(ofm, 128) * 128, full64 = ceil_div(ofm, 64) * 64;
+    return ofm * 5 < full128 * 4 && full64 < full128;
+}
+int channel_tiles(int ofm) { return half_mode(ofm) ? ceil_div(ofm, 64) : ceil_div(ofm, kM); }
+
+// one tile = 128 rows (TMEM lanes) x 64 B per K-block in both modes
 size_t tiles_bytes(int ifm, int ofm, int ksize)
 {
     const int nkb = ceil_div(ceil_div(ifm, 4) * ksize * ksize, kSteps);
-    return (size_t)ceil_div(ofm, kM) * nkb * kWBytes;
+    return (size_t)channel_tiles(ofm) * nkb * kWBytes;
 }
 
 }  // namespace
@@ -914,17 +947,18 @@ size_t tiles_bytes(int ifm, int ofm, int ksize)
 size_t wprep_tc2_bytes(int ifm, int ofm, int ksize)
 {
     const int nkb = ceil_div(ceil_div(ifm, 4) * ksize * ksize, kSteps);
-    return tiles_bytes(ifm, ofm, ksize) + (size_t)ceil_div(ofm, kM) * nkb * kM * sizeof(unsigned);
+    return tiles_bytes(ifm, ofm, ksize) + (size_t)channel_tiles(ofm) * nkb * kM * sizeof(unsigned);
 }
 
 void launch_wprep_tc2(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, int so, cudaStream_t st)
 {
     const int nkb = ceil_div(ceil_div(ifm, 4) * ksize * ksize, kSteps);
-    const long long total = (long long)ceil_div(ofm, kM) * nkb * kM * 32;
-    wprep_tc2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(blob, (unsigned char *)dst, ifm, ofm, ksize, TM, TN, nkb, so, total);
+    const int half = half_mode(ofm);
+    const long long total = (long long)channel_tiles(ofm) * nkb * kM * 32;
+    wprep_tc2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(blob, (unsigned char *)dst, ifm, ofm, ksize, TM, TN, nkb, so, total, half);
     const long long rows = total / 32;
     wnorm_tc2_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(blob, (unsigned *)((char *)dst + tiles_bytes(ifm, ofm, ksize)), ifm, ofm, ksize,
-                                                                      TM, TN, nkb, rows);
+                                                                      TM, TN, nkb, rows, half);
 }
 
 // the driver's tensor-map encoder without linking libcuda: resolved once through the runtime (thread-safe static initialisation)
@@ -940,9 +974,12 @@ static PFN_cuTensorMapEncodeTiled tensor_map_encoder()
 }
 
 // Fills the launch plan; false = the shape / shift / alignment is not eligible for the tensor-core path.
-static bool tc2_plan(const ConvFastParams &cp, int ksize, Tc2Params &p, size_t &smem, unsigned long long &frame_bytes)
+static bool tc2_plan(const ConvFastParams &cp, int ksize, Tc2Params &p, size_t &smem, unsigned long long &frame_bytes, bool &half)
 {
     if ((ksize != 1 && ksize != 3) || cp.so < 8 || cp.so > 22) return false;
+    half = half_mode(cp.OFM);
+    const int PTI = half ? Tc2Shape<true>::kPTI : Tc2Shape<false>::kPTI;                      // pixels per work item
+    const size_t fixed = half ? Tc2Shape<true>::kFixedBytes : Tc2Shape<false>::kFixedBytes;
     p = Tc2Params{};
     p.out = (int16_t *)cp.out; p.w = (const unsigned char *)cp.w; p.bias = (const int16_t *)cp.bias;
     p.wnorm = (const unsigned *)((const char *)cp.w + tiles_bytes(cp.G * 4, cp.OFM, ksize));
@@ -953,29 +990,29 @@ static bool tc2_plan(const ConvFastParams &cp, int ksize, Tc2Params &p, size_t &
     p.nkb = ceil_div(cp.G * ksize * ksize, kSteps);
     p.HW = cp.H * cp.W;
     const long long npix = (long long)cp.B * p.HW;
-    const long long npt = (npix + kPT - 1) / kPT;
-    const int mtiles = ceil_div(cp.OFM, kM);
+    const long long npt = (npix + PTI - 1) / PTI;
+    const int mtiles = channel_tiles(cp.OFM);
     if (npt * mtiles > 0x3fffffffLL || (long long)cp.G * p.HW > 0x7fffffffLL - 4096) return false;
     p.npt = (int)npt;
     p.mtiles = mtiles;
     p.nitems = (int)(npt * mtiles);
     // a pixel tile may straddle ONE frame boundary (two staged runs); frames smaller than a tile only as a single frame
-    if (p.HW < kPT && cp.B > 1) return false;
+    if (p.HW < PTI && cp.B > 1) return false;
     // the staged run of one (group, frame segment): every pixel the taps of 48 consecutive pixels touch, in boxes of <= 256 pixels
     // whose shared-memory destinations stay 128-byte aligned (16 pixels)
-    const int run = kPT + (ksize == 3 ? 2 * cp.W + 2 : 0) + 1;   // + 1: the run starts on an even pixel
+    const int run = PTI + (ksize == 3 ? 2 * cp.W + 2 : 0) + 1;   // + 1: the run starts on an even pixel
     p.nbox = ceil_div(run, 256);
     p.boxlen = (ceil_div(run, p.nbox) + 15) & ~15;
     p.seg_px = p.nbox * p.boxlen;
     const size_t per_group = (size_t)2 * p.seg_px * 8;
-    int gs = (int)((200 * 1024 - (size_t)kFixedBytes) / (2 * per_group));
+    int gs = (int)((200 * 1024 - fixed) / (2 * per_group));
     if (gs < 1) return false;
     int sh = 0;
     while ((2 << sh) <= gs && (2 << sh) <= 16) ++sh;   // largest power of two <= min(gs, 16)
     p.gs_shift = sh;
     gs = 1 << sh;
     p.nchunks = ceil_div(cp.G, gs);
-    smem = (size_t)kFixedBytes + 2 * per_group * gs;
+    smem = fixed + 2 * per_group * gs;
     if (smem < 120 * 1024) smem = 120 * 1024;          // one CTA per SM: a CTA allocates all 512 TMEM columns
     // tensor map over the C4 input as [frame][G*H*W] 8-byte pixels: 16-byte aligned base and frame stride
     frame_bytes = cp.B > 1 ? (unsigned long long)cp.in_frame_stride * 2 : (((unsigned long long)cp.G * p.HW * 8 + 15) & ~15ull);
@@ -990,7 +1027,8 @@ bool conv_i16_tc2_eligible(const ConvFastParams &cp_in, int ksize, int frames)
     Tc2Params p;
     size_t smem;
     unsigned long long fb;
-    return tc2_plan(cp, ksize, p, smem, fb) && tensor_map_encoder() != nullptr;
+    bool half;
+    return tc2_plan(cp, ksize, p, smem, fb, half) && tensor_map_encoder() != nullptr;
 }
 
 // Returns 1 when launched, -1 when the shape/shift is not eligible for the tensor-core path, -2 when the tensor map cannot be built.
@@ -999,7 +1037,8 @@ int launch_conv_i16_tc2(const ConvFastParams &cp, int ksize, cudaStream_t st, co
     Tc2Params p;
     size_t smem;
     unsigned long long frame_bytes;
-    if (!tc2_plan(cp, ksize, p, smem, frame_bytes)) return -1;
+    bool half;
+    if (!tc2_plan(cp, ksize, p, smem, frame_bytes, half)) return -1;
     const PFN_cuTensorMapEncodeTiled encode = tensor_map_encoder();
     if (!encode) return -2;
     alignas(64) CUtensorMap tmap;
@@ -1018,7 +1057,8 @@ int launch_conv_i16_tc2(const ConvFastParams &cp, int ksize, cudaStream_t st, co
     nsm = Y2_TC2_GRID;                                  // experiments: fewer / more persistent CTAs than SMs
 #endif
     dim3 grid((unsigned)(p.nitems < nsm ? p.nitems : nsm));
-    const bool ok = ksize == 3 ? dispatch_so<3>(p, tmap, cp.so, grid, smem, st) : dispatch_so<1>(p, tmap, cp.so, grid, smem, st);
+    const bool ok = ksize == 3 ? (half ? dispatch_so<3, true>(p, tmap, cp.so, grid, smem, st) : dispatch_so<3, false>(p, tmap, cp.so, grid, smem, st))
+                               : (half ? dispatch_so<1, true>(p, tmap, cp.so, grid, smem, st) : dispatch_so<1, false>(p, tmap, cp.so, grid, smem, st));
     if (!ok) return -1;
 #ifdef Y2_TC2_PROFILE
     {
@@ -1054,7 +1094,7 @@ int launch_conv_i16_tc2(const ConvFastParams &cp, int ksize, cudaStream_t st, co
         }
     }
 #endif
-    if (variant) *variant = ksize == 3 ? "conv_i16_tc2<3>" : "conv_i16_tc2<1>";
+    if (variant) *variant = ksize == 3 ? (half ? "conv_i16_tc2<3,half>" : "conv_i16_tc2<3>") : (half ? "conv_i16_tc2<1,half>" : "conv_i16_tc2<1>");
     return 1;
 }
 

@@ -215,9 +215,16 @@ def yolov2_cuda_ps(net: _cfg.Network, input: np.ndarray, pack: WeightsPack, devi
         y.close()
 
 
-def _on_tensor_cores(l) -> bool:
-    """csrc/capi.cu auto policy: 128-channel tiles at least 80 % full and a deep enough chain"""
-    return l.n * 5 >= -(-l.n // 128) * 128 * 4 and ((l.size == 3 and l.c >= 64) or (l.size == 1 and l.c >= 128))
+def _tensor_core_tile(l):
+    """csrc/capi.cu auto policy: (channels per work item, pixels per work item) of the tcgen05 kernel, or None for the CUDA-core
+    kernel.  128-channel tiles at least 80 % full, or 64-channel tiles x two pixel sets when those fill better (half_mode)."""
+    up = lambda n, m: -(-n // m) * m
+    fill128, fill64 = l.n * 5 >= up(l.n, 128) * 4, l.n * 5 >= up(l.n, 64) * 4
+    deep = (l.size == 3 and l.c >= 32) or (l.size == 1 and l.c >= 128)
+    if not deep or not (fill128 or fill64):
+        return None
+    half = l.n * 5 < up(l.n, 128) * 4 and up(l.n, 64) < up(l.n, 128)
+    return (64, 96) if half else (128, 48)
 
 
 def pass_efficiency(net: _cfg.Network, n: int, sms: int = 148) -> float:
@@ -231,8 +238,9 @@ def pass_efficiency(net: _cfg.Network, n: int, sms: int = 148) -> float:
         if l.type != _cfg.CONV:
             continue
         steps = math.ceil(l.c / 4) * l.size * l.size
-        if _on_tensor_cores(l):
-            units, slots, cost = math.ceil(n * l.h * l.w / 48) * math.ceil(l.n / 128), sms, steps * 48 * 128
+        tile = _tensor_core_tile(l)
+        if tile:
+            units, slots, cost = math.ceil(n * l.h * l.w / tile[1]) * math.ceil(l.n / tile[0]), sms, steps * 48 * 128
         else:
             tp = 13 if l.w % 13 == 0 else 7
             sw = -(-l.w // tp)
