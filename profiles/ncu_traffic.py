@@ -27,7 +27,7 @@ tot = sum(a[1] for a in agg.values())
 print(f"{'kernel':70s} {'launches':>8s} {'ms':>10s} {'share':>7s} {'DRAM MB/launch':>15s} {'DRAM GB/s':>10s}")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{k[:70]:70s} {a[0]:8d} {a[1]:10.3f} {a[1] / tot:7.3f} {a[2] / a[0] / 1e6:15.2f} {a[2] / (a[1] * 1e-3) / 1e9 if a[1] else 0:10.1f}")
-dom = [(k, a) for k, a in agg.items() if re.match(r"conv_i16_tc2_kernel<3", k)]
+dom = [(k, a) for k, a in agg.items() if re.match(r"conv_i16_tc2_kernel<3, \d+, 0>", k)]      # 3x3, 128-channel items (not the HALF instantiation)
 if dom and len(sys.argv) > 3:
     n = sum(a[0] for _, a in dom)
     out = {"kernel_prefix": "conv_i16_tc2_kernel<3", "frames_per_step": int(sys.argv[2]), "launches": n,

@@ -815,7 +815,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                         int a = Uo[j] - 32768;
                         if (p.leaky && a < 0) a = a / 10;
                         amax = max(amax, a < 0 ? -a : a);
+#ifndef Y2_TC2_NOSTORE
                         om[off] = (int16_t)a;
+#else
+                        if (a == 0x7fffff) om[off] = (int16_t)a;      // experiment: what do the scattered 2-byte stores cost?
+#endif
                     }
                 }
             }
