@@ -801,30 +801,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                     PROF_TL(gb * kR + r, 12 + q4);
                 }
             }
-            // ---- the item's 12 pixels of this thread's channel: leaky, store, largest |output| ----
-            if (m < p.OFM) {
+            // ---- the item's 12 pixels of this thread's channel: leaky, largest |output|, store.  The four lanes of a channel quad
+            // (channels 4k..4k+3 = one C4 word) transpose their 4 channels x 4 pixels through two shuffle stages, so that lane q of
+            // the quad stores the complete 8-byte word of pixel q: one STG.64 per tile instead of four scattered STG.U16, and the
+            // quad's four words are one full 32-byte sector (the 2-byte stores cost 1.6 % of a forward: -DY2_TC2_NOSTORE experiment)
+            {
                 const long long *oo = outoff + (n & (kTabSlots - 1)) * kPTI + pset * kPT;
-                int16_t *om = p.out + ((long long)(m >> 2) * p.HW * 4 + (m & 3));
+                int16_t *om = p.out + (long long)(m >> 2) * p.HW * 4;          // the quad's C4 word plane (m >> 2 is the same for its four lanes)
+                const int cq = lane & 3;
+                const bool mvalid = m < p.OFM;
 #pragma unroll
                 for (int rr = 0; rr < kTPG; ++rr) {
-                    const int (&Uo)[kPx] = UR[rr];
+                    int v[kPx];
 #pragma unroll
                     for (int j = 0; j < kPx; ++j) {
-                        const long long off = oo[(kGroups * rr + kg) * kPx + j];
-                        if (off < 0) continue;
-                        int a = Uo[j] - 32768;
+                        int a = UR[rr][j] - 32768;
                         if (p.leaky && a < 0) a = a / 10;
-                        amax = max(amax, a < 0 ? -a : a);
+                        if (!mvalid) a = 0;                                     // channels beyond OFM: the padding of the last C4 word stays zero
+                        v[j] = a;
+                    }
+                    {
+                        const int x0 = (cq & 2) ? v[0] : v[2], x1 = (cq & 2) ? v[1] : v[3];
+                        const int r0 = __shfl_xor_sync(0xffffffffu, x0, 2), r1 = __shfl_xor_sync(0xffffffffu, x1, 2);
+                        if (cq & 2) { v[0] = r0; v[1] = r1; } else { v[2] = r0; v[3] = r1; }
+                        const int y0 = (cq & 1) ? v[0] : v[1], y1 = (cq & 1) ? v[2] : v[3];
+                        const int s0 = __shfl_xor_sync(0xffffffffu, y0, 1), s1 = __shfl_xor_sync(0xffffffffu, y1, 1);
+                        if (cq & 1) { v[0] = s0; v[2] = s1; } else { v[1] = s0; v[3] = s1; }
+                    }
+                    // v[c] = channel (m & ~3) + c of pixel cq
+                    const long long off = oo[(kGroups * rr + kg) * kPx + cq];
+                    if (off >= 0 && (m & ~3) < p.OFM) {                        // (a quad entirely beyond OFM has no word in the output tensor)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) amax = max(amax, v[c] < 0 ? -v[c] : v[c]);
 #ifndef Y2_TC2_NOSTORE
-                        om[off] = (int16_t)a;
-#else
-                        if (a == 0x7fffff) om[off] = (int16_t)a;      // experiment: what do the scattered 2-byte stores cost?
+                        *reinterpret_cast<uint2 *>(om + off) = make_uint2(__byte_perm((unsigned)v[0], (unsigned)v[1], 0x5410), __byte_perm((unsigned)v[2], (unsigned)v[3], 0x5410));
 #endif
                     }
                 }
             }
             mt = mt_next;
             wn = wn_next;
+            PROF_ADD(5);                            // (profile build: slot 5 = the per-item output store + re-initialisation)
         }
         PROF_END;
         if (p.xmax_out) {
