@@ -192,6 +192,11 @@ int yolo2cuda_net_layer_times(yolo2cuda_net *net, float *ms, int n_layers);
  * never NULL).  Diagnostics / tests: lets a parity test assert WHICH conv kernel produced the bits it compared. */
 const char *yolo2cuda_net_layer_kernel(const yolo2cuda_net *net, int layer);
 
+/* Diagnostics: y[i] = exp(x[i]) exactly as the region kernel computes the logistic / softmax exponentials of
+ * src/core/yolo_math.cpp:19,234 - glibc's double exp algorithm restated on the device (sysdeps/ieee754/dbl-64/e_exp.c, FMA form),
+ * bit-identical to the libm of an x86-64 host with FMA.  DEVICE pointers, asynchronous on the context stream. */
+int yolo2cuda_selftest_exp_dev(yolo2cuda_ctx *ctx, const double *x, double *y, size_t n);
+
 /* ---- detections: get_network_boxes + do_nms_sort on the host (src/core/yolo_region.cpp:169-236,
  * src/core/yolo_post.cpp:54-85).  region: one frame's region tensor (HOST).  The output arrays must hold
  * lw*lh*n entries (the worst case); the function fills the first K of them, K = the number of candidates with

@@ -82,6 +82,13 @@ class Oracle:
         self.lib.orc_round_shift.restype = C.c_int64
         self.lib.orc_round_shift.argtypes = [C.c_int64, C.c_int]
 
+    def libm_exp(self, x):
+        """the host libm's double exp, element-wise (NOT numpy's own SIMD exp)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        self.lib.orc_libm_exp(_vp(x), _vp(y), C.c_long(x.size))
+        return y
+
     def letterbox_u8(self, img, net_w, net_h):
         """img: uint8 [h][w][c] (stb layout) -> float32 [c][net_h][net_w]"""
         img = np.ascontiguousarray(img, dtype=np.uint8)

@@ -680,3 +680,9 @@ int orc_letterbox_u8(const unsigned char *hwc, int iw, int ih, int ic, float *ou
     free(im); free(part); free(res);
     return 0;
 }
+
+/* the host libm's exp on an array: what the reference's logistic_activate / softmax evaluate (src/core/yolo_math.cpp:19,234) */
+void orc_libm_exp(const double *x, double *y, long n)
+{
+    for (long i = 0; i < n; ++i) y[i] = exp(x[i]);
+}

@@ -109,6 +109,7 @@ int orc_net_forward_f32(const orc_layer *layers, int n_layers, const float *fram
                         const float *w_reorg, const float *bias, float **dump, float *region_out);
 
 /* stb u8 [ih][iw][ic] image -> float [ic][net_h][net_w] letterboxed network input (yolo_image.cpp:84-165,178-187) */
+void orc_libm_exp(const double *x, double *y, long n);
 int orc_letterbox_u8(const unsigned char *hwc, int iw, int ih, int ic, float *out, int net_w, int net_h);
 
 /* reference build parameters Tn (rounding group) / Tm used by orc_net_forward_* (defaults 4 / 32) */

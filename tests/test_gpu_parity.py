@@ -1,12 +1,13 @@
 """GPU parity tests: the CUDA path, called through the C ABI, against the oracle on the same
 seeded inputs.  Bar: bit-exact for int16; 1e-4 relative (of the layer's max |value|) for fp32."""
+import ctypes as C
 import os
 
 import numpy as np
 import pytest
 
 from helpers import accel_call, align8, make_conv_case, oracle_conv, valid
-from yolo2_b200 import cfg as ycfg, weights as yw
+from yolo2_b200 import _capi, cfg as ycfg, weights as yw
 from yolo2_b200.accel import pool_call_args
 from yolo2_b200.model import Yolo2Net
 
@@ -748,3 +749,22 @@ def test_host_forward_pass_schedule_is_invisible(oracle):
         assert np.array_equal(np.ascontiguousarray(outs[0][10]).reshape(-1).view(np.uint32), np.asarray(want, np.float32).reshape(-1).view(np.uint32))
     finally:
         y.close()
+
+
+def test_device_exp_equals_host_libm(accel16, oracle):
+    """glibc_exp in csrc/bw_ops.cu (the exponential of the region head's logistic and softmax) against the host libm's exp on 2^21
+    inputs - the region head's range, float-valued arguments, |x| up to 1100 (scaled special cases, over- and underflow) and
+    arbitrary bit patterns - bit for bit (NaN payloads aside)."""
+    import torch
+    rng = np.random.default_rng(7)
+    n = 1 << 19
+    x = np.concatenate([rng.uniform(-40, 40, n), rng.uniform(-90, 90, n).astype(np.float32).astype(np.float64),
+                        rng.uniform(-1100, 1100, n), rng.integers(0, 2 ** 64, n, dtype=np.uint64).view(np.float64),
+                        np.array([0.0, -0.0, np.inf, -np.inf, 709.78, -745.2, 1e-300, -1e-300, 512.0, -512.0, 1024.0, -1075.0])])
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    _capi.check(accel16.ctx, accel16.lib.yolo2cuda_selftest_exp_dev(accel16.ctx, C.c_void_p(xd.data_ptr()), C.c_void_p(yd.data_ptr()), x.size))
+    accel16.synchronize()
+    got, want = yd.cpu().numpy(), oracle.libm_exp(x)
+    both_nan = np.isnan(got) & np.isnan(want)
+    assert np.array_equal(got.view(np.uint64)[~both_nan], want.view(np.uint64)[~both_nan])

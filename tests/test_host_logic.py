@@ -2,6 +2,7 @@
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -202,3 +203,27 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+def test_glibc_exp_restatement_matches_libm(tmp_path):
+    """oracle/exp_check.c: the restatement of glibc's double exp (FMA form, data from glibc_exp_data.h) that the CUDA region kernel
+    uses for the logistic and the softmax equals the host libm's exp (what the reference's yolo_math.cpp calls) on 2^22 inputs -
+    the region head's range, float-valued arguments, the scaled special cases, arbitrary bit patterns - bit for bit."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(tmp_path, "exp_check")
+    subprocess.check_call(["gcc", "-O2", "-fno-builtin", "-ffp-contract=off", "-o", exe, os.path.join(root, "oracle", "exp_check.c"), "-lm"])
+    out = subprocess.run([exe, str(1 << 22)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "0", (out.stdout, out.stderr)
+
+
+def test_glibc_exp_data_header_matches_this_libm(tmp_path):
+    """the committed csrc/glibc_exp_data.h is what csrc/gen_glibc_exp_data.py reads out of the libm the tests run with"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libm = "/lib/x86_64-linux-gnu/libm.so.6"
+    if not os.path.exists(libm):
+        pytest.skip("no x86-64 glibc libm at the usual path")
+    out = os.path.join(tmp_path, "h.h")
+    subprocess.check_call([sys.executable, os.path.join(root, "yolo-fpga-accelerator_b200", "csrc", "gen_glibc_exp_data.py"), libm, out])
+    assert open(out).read() == open(os.path.join(root, "yolo-fpga-accelerator_b200", "csrc", "glibc_exp_data.h")).read()

@@ -7,7 +7,9 @@
 // element; nothing is re-read.
 #include <cfloat>
 
+#include <math_constants.h>
 #include "common.cuh"
+#include "glibc_exp_data.h"
 
 namespace y2 {
 
@@ -306,7 +308,57 @@ __global__ void reorg_driver_c4_kernel(const T *__restrict__ in, T *__restrict__
         *reinterpret_cast<typename Vec4<T>::type *>(v);
 }
 
-__device__ __forceinline__ float logistic_ref(float x) { return (float)(1. / (1. + exp((double)(-x)))); }  // yolo_math.cpp:19
+// glibc's double exp restated (sysdeps/ieee754/dbl-64/e_exp.c of glibc >= 2.28, N = 128 table + degree-5 polynomial, in the FMA form
+// the x86-64 ifunc selects on every CPU with FMA; data in glibc_exp_data.h, generated from the host's libm by
+// gen_glibc_exp_data.py).  The reference's logistic_activate and softmax call exp(double) (yolo_math.cpp:19,234): with this
+// the region head reproduces the host's bits by construction (the checker's exp_check.c: 0 differences against libm on 10^8 inputs
+// incl. arbitrary bit patterns); CUDA's own exp may differ by 1 ulp.  Every operation is one explicitly rounded instruction.
+__device__ const unsigned long long g_glibc_exp_tab[256] = {Y2_GLIBC_EXP_TAB};
+__device__ __forceinline__ double glibc_exp(double x)
+{
+    unsigned abstop = (unsigned)((unsigned long long)__double_as_longlong(x) >> 52) & 0x7ffu;
+    if (abstop - 0x3c9u >= 0x3fu) {                        // |x| < 2^-54, |x| >= 512, inf or NaN
+        if (abstop - 0x3c9u >= 0x80000000u) return __dadd_rn(1.0, x);
+        if (abstop >= 0x409u) {                            // |x| >= 1024
+            if (__double_as_longlong(x) == __double_as_longlong(-CUDART_INF)) return 0.0;
+            if (abstop >= 0x7ffu) return __dadd_rn(1.0, x);
+            return (__double_as_longlong(x) < 0) ? 0.0 : CUDART_INF;       // __math_uflow / __math_oflow
+        }
+        abstop = 0;
+    }
+    double kd = __fma_rn(Y2_GLIBC_EXP_INVLN2N, x, Y2_GLIBC_EXP_SHIFT);
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd = __dsub_rn(kd, Y2_GLIBC_EXP_SHIFT);
+    const double r = __fma_rn(kd, Y2_GLIBC_EXP_NEGLN2LON, __fma_rn(kd, Y2_GLIBC_EXP_NEGLN2HIN, x));
+    const unsigned idx = 2u * (unsigned)(ki & 127ull);
+    const double tail = __longlong_as_double((long long)g_glibc_exp_tab[idx]);
+    unsigned long long sbits = g_glibc_exp_tab[idx + 1] + (ki << 45);
+    const double r2 = __dmul_rn(r, r);
+    const double tmp = __fma_rn(__dmul_rn(r2, r2), __fma_rn(r, Y2_GLIBC_EXP_C5, Y2_GLIBC_EXP_C4),
+                                __fma_rn(__fma_rn(r, Y2_GLIBC_EXP_C3, Y2_GLIBC_EXP_C2), r2, __dadd_rn(tail, r)));
+    if (abstop == 0) {                                     // 512 <= |x| < 1024: the scale would over- / underflow (specialcase())
+        if ((ki & 0x80000000ull) == 0) {
+            sbits -= 1009ull << 52;
+            const double scale = __longlong_as_double((long long)sbits);
+            return __dmul_rn(0x1p1009, __fma_rn(scale, tmp, scale));
+        }
+        sbits += 1022ull << 52;
+        const double scale = __longlong_as_double((long long)sbits), st = __dmul_rn(scale, tmp);
+        double y = __dadd_rn(scale, st);
+        if (y < 1.0) {
+            double lo = __dadd_rn(__dsub_rn(scale, y), st);
+            const double hi = __dadd_rn(1.0, y);
+            lo = __dadd_rn(__dadd_rn(__dsub_rn(1.0, hi), y), lo);
+            y = __dsub_rn(__dadd_rn(hi, lo), 1.0);
+            if (y == 0.0) y = 0.0;
+        }
+        return __dmul_rn(0x1p-1022, y);
+    }
+    const double scale = __longlong_as_double((long long)sbits);
+    return __fma_rn(scale, tmp, scale);
+}
+
+__device__ __forceinline__ float logistic_ref(float x) { return (float)__ddiv_rn(1., __dadd_rn(1., glibc_exp((double)(-x)))); }  // yolo_math.cpp:19
 
 // One thread per (frame, anchor, cell): strip + dequantise + logistic(x,y,obj) + class softmax.
 template <typename T, int LAYOUT>
@@ -350,7 +402,7 @@ __global__ void region_kernel(const T *__restrict__ in, float *__restrict__ out,
         float sum = 0;
         for (int i = 0; i < nc; ++i) {
             float arg = __fsub_rn(__fdiv_rn(fetch(first + i), 1.0f), __fdiv_rn(largest, 1.0f));
-            float e = (float)exp((double)arg);
+            float e = (float)glibc_exp((double)arg);
             sum = __fadd_rn(sum, e);
             o[(long long)(first + i) * wh] = e;
         }
@@ -520,6 +572,14 @@ __global__ void letterbox_kernel(const unsigned char *__restrict__ src, float *_
         out[(size_t)k * per + rem] = v;
     }
 }
+
+// diagnostics: the restated exp on an array (the tests compare it with the host libm bit for bit)
+__global__ void glibc_exp_kernel(const double *__restrict__ x, double *__restrict__ y, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = glibc_exp(x[i]);
+}
+void launch_glibc_exp(const double *x, double *y, long long n, cudaStream_t st) { glibc_exp_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, y, n); }
 
 void launch_letterbox(const unsigned char *src, float *dst, int B, int iw, int ih, int ic, int net_w, int net_h, cudaStream_t st)
 {

@@ -1117,6 +1117,16 @@ int yolo2cuda_net_forward_host(yolo2cuda_net *net, const float *frames, int batc
     return YOLO2CUDA_SUCCESS;
 }
 
+int yolo2cuda_selftest_exp_dev(yolo2cuda_ctx *ctx, const double *x, double *y, size_t n)
+{
+    if (!ctx || !x || !y || n == 0) return YOLO2CUDA_ERROR;
+    CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    launch_glibc_exp(x, y, (long long)n, ctx->stream);
+    ctx->launches += 1;
+    CUDA_OK(ctx, cudaGetLastError());
+    return YOLO2CUDA_SUCCESS;
+}
+
 int yolo2cuda_letterbox_dev(yolo2cuda_ctx *ctx, const unsigned char *src, int batch, int iw, int ih, int ic, float *dst,
                             int net_w, int net_h)
 {

@@ -107,6 +107,8 @@ int launch_detect(const float *region, float *boxes, float *probs, float *object
 void launch_compact_detections(const float *boxes, const float *probs, const float *objectness, int B, int total, int classes, int cap,
                                unsigned *records, int *counts, cudaStream_t st);
 // stb u8 [B][ih][iw][ic] -> float [B][ic][net_h][net_w], darknet letterbox (yolo_image.cpp:84-165,178-187), bit-exact
+// glibc's double exp as the region kernel computes it, element-wise on device arrays (diagnostics / tests)
+void launch_glibc_exp(const double *x, double *y, long long n, cudaStream_t st);
 void launch_letterbox(const unsigned char *src, float *dst, int B, int iw, int ih, int ic, int net_w, int net_h, cudaStream_t st);
 void launch_reorg_driver_planar(const void *in, void *out, int c, int h, int w, int shift, int elem_bytes, cudaStream_t st);
 void launch_reorg_driver_c4(const void *in, void *out, int B, int c, int h, int w, int shift,

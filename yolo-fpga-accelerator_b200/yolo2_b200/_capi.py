@@ -55,6 +55,7 @@ SYMBOLS = {
                                              C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "yolo2cuda_net_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo2cuda_net_forward_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "yolo2cuda_selftest_exp_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "yolo2cuda_letterbox_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "yolo2cuda_net_forward_images_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "yolo2cuda_net_get_layer_output": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
