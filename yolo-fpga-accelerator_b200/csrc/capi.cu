@@ -30,6 +30,7 @@ struct yolo2cuda_ctx {
     int use_tc = -1;  // YOLO2CUDA_TC: unset = auto (the tcgen05 kernel csrc/conv_i16_tc2.cu on the layers where it measured faster),
                       // 0 = CUDA-core kernels only, anything else = the tcgen05 kernel wherever the shape is eligible (tests / profiling)
     int tc_min_ofm = 96;
+    int use_g1 = 1;                  // YOLO2CUDA_G1=0: the generic C4 kernel (and a separate pool launch) for one-group 3x3 layers (A/B measurements)
     int tc_force_exact = 0;          // YOLO2CUDA_TC_EXACT=1: the tcgen05 kernel never takes its no-saturation fast path (tests)
     unsigned long long *d_tc_stats = nullptr;   // device [2]: warp-tiles of the tcgen05 kernel through the fast / the exact path
     // growable device scratch for the per-layer entry points
@@ -224,6 +225,7 @@ int yolo2cuda_create(yolo2cuda_ctx **out, int device, int precision)
     const char *tc = getenv("YOLO2CUDA_TC");
     ctx->use_tc = (tc && tc[0]) ? (tc[0] == '0' ? 0 : 2) : -1;
     if (const char *mo = getenv("YOLO2CUDA_TC_MIN_OFM")) ctx->tc_min_ofm = atoi(mo);
+    if (const char *g1 = getenv("YOLO2CUDA_G1")) ctx->use_g1 = g1[0] != '0';
     const char *ex = getenv("YOLO2CUDA_TC_EXACT");
     ctx->tc_force_exact = (ex && ex[0] && ex[0] != '0') ? 1 : 0;
     if (cudaMalloc(&ctx->d_tc_stats, 2 * sizeof(unsigned long long)) != cudaSuccess ||
@@ -457,6 +459,9 @@ struct LayerPlan {
     void *w_tc = nullptr;          // tcgen05 operand tiles (tensor-core path)
     bool tc = false;
     bool tc32 = false;             // Tn = 32 build: csrc/conv_i16_tc32.cu
+    bool g1 = false;               // one input channel group (IFM <= 4), 3x3: csrc/conv_i16_g1.cu
+    bool pool_fusable = false;     //   ... and the next layer is a 2x2 / stride-2 max-pool of even dims that only reads this layer
+    bool fused_away = false;       // max-pool layer whose work the previous conv launch did (set per forward)
     int Qw = 0, Qa_in = 0, Qa_out = 0, Qb = 0;
     int reorg_shift = 0;
     int region_q = 0;
@@ -654,6 +659,16 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
                 if (l.tc) {
                     p.w = l.w_tc;
                     n = launch_conv_i16_tc2(p, l.d.size, st, &l.variant);
+                } else if (l.g1) {
+                    // fused with the max-pool that follows unless every layer's output has to survive (debug keep-all mode)
+                    const bool pool = l.pool_fusable && !net->keep_all;
+                    if (pool) {
+                        LayerPlan &nx = net->L[i + 1];
+                        p.out = nx.out.base;
+                        p.out_frame_stride = nx.out.frame_stride;
+                        nx.fused_away = true;
+                    }
+                    n = launch_conv_i16_g1(p, l.d.size, pool, st, &l.variant);
                 } else {
                     n = e == 2 ? launch_conv_i16_fast(p, l.d.size, st, &l.variant) : launch_conv_f32_fast(p, l.d.size, st, &l.variant);
                 }
@@ -685,6 +700,11 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
             break;
         }
         case YOLO2CUDA_MAXPOOL:
+            if (l.fused_away) {       // the previous conv launch pooled in its store (csrc/conv_i16_g1.cu)
+                l.fused_away = false;
+                l.variant = "(fused into the conv store)";
+                break;
+            }
             launch_maxpool_c4(l.in.base, l.out.base, B, ceil_div(l.d.c, 4), l.d.stride, l.d.w, l.d.h, l.d.out_w, l.d.out_h,
                               l.in.frame_stride, l.out.frame_stride, e, st);
             l.variant = "maxpool_c4";
@@ -829,6 +849,12 @@ int yolo2cuda_net_create(yolo2cuda_ctx *ctx, const yolo2cuda_layer_desc *layers,
     for (int i = 0; i < n_layers; ++i)
         if (layers[i].type == YOLO2CUDA_ROUTE && tensor_of[i] >= 0)
             net->T[tensor_of[i]].last_use = std::max(net->T[tensor_of[i]].last_use, i);
+    // A max-pool that may be fused into the store of the one-group 3x3 conv before it (csrc/conv_i16_g1.cu) is WRITTEN while that
+    // conv runs: its output becomes live one layer early, so that the arena never packs it over the conv's own input.
+    for (int i = 0; i + 1 < n_layers; ++i)
+        if (layers[i].type == YOLO2CUDA_CONV && layers[i].size == 3 && layers[i].c <= 4 && layers[i + 1].type == YOLO2CUDA_MAXPOOL &&
+            tensor_of[i + 1] >= 0)
+            net->T[tensor_of[i + 1]].first_def = std::min(net->T[tensor_of[i + 1]].first_def, i);
     for (auto &t : net->T)
         if (t.bytes && t.last_use < t.first_def) t.last_use = t.first_def;       // written, never read: still needs a home
     net->tensor_out = tensor_of;
@@ -984,6 +1010,16 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                         if (!l.w_tc && (rc = net_alloc(net, &l.w_tc, wprep_tc2_bytes(l.d.c, l.d.n, l.d.size)))) return rc;
                         launch_wprep_tc2((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, so, st);
                         ctx->launches += 1;
+                    }
+                    // a 3x3 layer with one input channel group (YOLOv2's first layer): the specialised kernel, which can also do the
+                    // 2x2 / stride-2 max-pool that follows in its store (only when nothing else reads this layer's output)
+                    l.g1 = !l.tc && e == 2 && ctx->use_g1 && l.d.size == 3 && l.d.c <= 4;
+                    l.pool_fusable = false;
+                    if (l.g1 && i + 1 < net->L.size()) {
+                        const yolo2cuda_layer_desc &nx = net->L[i + 1].d;
+                        l.pool_fusable = nx.type == YOLO2CUDA_MAXPOOL && nx.size == 2 && nx.stride == 2 && !(l.d.out_h & 1) && !(l.d.out_w & 1) &&
+                                         nx.out_h == l.d.out_h / 2 && nx.out_w == l.d.out_w / 2 && net->tensor_in[i + 1] == net->tensor_out[i] &&
+                                         net->tensor_out[i] >= 0 && net->T[net->tensor_out[i]].last_use == (int)i + 1 && net->concat_of[i] < 0;
                     }
                 }
             }

@@ -69,6 +69,8 @@ struct ConvFastParams {
 // Returns the number of kernels launched, or -1 when the shape is not eligible.
 int launch_conv_i16_fast(const ConvFastParams &p, int ksize, cudaStream_t st, const char **variant);
 int launch_conv_f32_fast(const ConvFastParams &p, int ksize, cudaStream_t st, const char **variant);
+// 3x3 conv of a layer with one input channel group (IFM <= 4), optionally with the following 2x2 / stride-2 max-pool fused (csrc/conv_i16_g1.cu)
+int launch_conv_i16_g1(const ConvFastParams &p, int ksize, int pool, cudaStream_t st, const char **variant);
 size_t conv_fast_plan(ConvFastParams &p, int ksize, int elem_bytes);  // fills SW/RB/PW/GS, returns smem bytes (0 = not eligible)
 
 void launch_wprep_i16(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, cudaStream_t st);
