@@ -1,4 +1,4 @@
-// INT16 convolution on the 5th-generation tensor cores (tcgen05 + TMEM), bit-exact - pipeline v2.
+// INT16 convolution on the 5th-generation tensor cores (tcgen05 + TMEM), bit-exact: a persistent, TMA-staged kernel.
 //
 // Arithmetic (hls/core/core_compute.cpp:65-120): every (4-channel group x tap) step of the reference's
 // chain is  acc = clamp16(acc + ((P + half) >> so)),  P = sum_{t<4} w_t * x_t.  Each int16 operand is
@@ -7,39 +7,36 @@
 // with P + half = 65536*HH + 256*M + LL.  One MMA K-slice (32) holds seven consecutive steps as a
 // block-diagonal activation operand, so every TMEM column is one exact 4-MAC partial sum.
 //
-// What changed against csrc/conv_i16_tc.cu (the first tcgen05 version):
-//  * weights are the A operand FROM TENSOR MEMORY (tcgen05.mma [d],[a],b-desc): an N=32..48 MMA with
-//    A in shared memory re-reads 4 KB of weights per instruction and is shared-memory bound;
-//    the epilogue warps copy each 8 KB K-block smem -> registers -> TMEM (tcgen05.st) once per K-block;
-//  * N = 32 (8 step slots x 4 pixels) and FIVE 96-column accumulator buffers instead of three 144-column
-//    ones: an epilogue warp loads a whole tile (tcgen05.ld x16 x 6) and releases the buffer before it
-//    computes, so the MMA of a buffer's next tile overlaps three tiles of epilogue work;
-//  * a 4-instruction step for 8 <= so <= 16 (so is a template parameter; LEA.HI needs an immediate):
+// Structure (DESIGN.md section 4 has the measurements behind every choice):
+//  * PERSISTENT: one CTA per SM walks work items (48 consecutive pixels x 128 output channels; HALF mode: 96 pixels x 64
+//    channels on the two halves of every lane quadrant) in a static round-robin; TMEM, barriers and rings are set up once and
+//    every pipeline counter runs on across items.
+//  * Roles, 24 warps: 16 epilogue warps in four groups (thread = one TMEM lane = one output channel, 96 registers), three builder
+//    warps (block-diagonal hi / lo operand tiles from the staged activation runs, a tile pair per barrier), one TMA producer warp
+//    (tensor-map boxes of the activation runs two chunks ahead + the per-item pixel tables), four MMA issuer warps (one elected
+//    lane each; they also move each 8 KB weight K-block shared memory -> registers -> TMEM, where it is the A operand:
+//    tcgen05.mma [d],[a],b-desc - an N = 32 MMA with A in shared memory re-reads 4 KB per instruction and is smem bound).
+//  * N = 32 (8 step slots x 4 pixels) and FIVE 96-column accumulator buffers (HH | M | LL): an epilogue warp reads a whole tile
+//    and releases the buffer before it computes, so the MMAs of a buffer's next tile overlap the epilogue work.
+//  * The exact step for 8 <= so <= 16 (so is a template parameter; LEA.HI needs an immediate):
 //       t = 256*M + LL            IMAD   (fits: |256 M| < 2^27, 0 <= LL < 2^19)
-//       a = HH * 2^(16-so) + acc  IMAD / LEA   (65536*HH is a multiple of 2^so: no rounding involved)
-//       a = a + (t >> so)         LEA.HI.SX32
-//       acc = max(min(a, 65535), 0)   VIMNMX.RELU   (acc is kept as acc+32768)
+//       d = HH * 2^(16-so) + (t >> so)   IMAD / LEA.HI.SX32   (65536*HH is a multiple of 2^so: no rounding involved)
+//       acc = max(min(acc + d, 65535), 0)   VIADDMNMX.RELU   (acc is kept as acc+32768)
 //    and for 17 <= so <= 22:  c = 256*HH + M; c += LL >> 8; a = acc + (c >> (so-8)); clamp.
-//    Measured issue cost (profiles/microbench/tc_epilogue_rates.cu): 4.55 cycles per warp-step per SMSP
-//    against 6.27 for the 5-instruction scaled step of v1 and ~9.9 for the CUDA-core kernel.
-//  * (end of round 1) the kernel turned out to be bound by the ISSUE SLOTS of the SM sub-partitions (ncu: 80 % busy, 4 of 7 executed
-//    instructions useful), so the instruction count was cut: warp-uniform role / TMEM addressing (shuffle-broadcast warp index),
-//    one address operand per plane read-out, predicated barrier arrives, and for so = 14..16 a THREE-instruction step - the HH
-//    product is issued 2^(16-so) times into its accumulator, TMEM delivers HH*2^(16-so), and  a = HHs + (t >> so)  is one
-//    LEA.HI.SX32.  4.17 -> 5.03 T steps/s on the 13x13x1024 layers; DESIGN.md section 4, profiles/r1_tc2_handoff_experiments.md.
-//  * four epilogue groups (chain state in shared memory between tiles) and a read-out handshake (rd_done[]) that makes the barrier
-//    ring phase-safe: no barrier can complete a second phase before every waiter has tested the first.
-//  * (round 2) NO-SATURATION FAST PATH.  65536*HH is a multiple of 2^so for so <= 16, so HH enters the chain linearly; if no step
+//  * NO-SATURATION FAST PATH.  65536*HH is a multiple of 2^so for so <= 16, so HH enters the chain linearly; if no step
 //    of a K-block can saturate, its seven steps collapse to   acc += 2^(16-so) * sum_s HH_s + sum_s ((256 M_s + LL_s) >> so):
 //    TWO instructions per step (IMAD, LEA.HI.SX32), and the HH plane is not read at all - the builders add a DENSE column per pixel
 //    (all seven steps' hi bytes) in the four spare columns 28..31 of the activation tile, so the HH MMA delivers sum_s HH_s there.
 //    "Cannot saturate" is decided per (output channel, pixel, K-block) from the accumulator itself:
 //        Dsum <= acc+32768 <= 65535 - Dsum,   Dsum = ((sum_{28 weights} |w|) * xmax >> so) + 8  >=  sum_s |rs(P_s, so)|
 //    with xmax = the largest |activation| of the layer input (an atomicMax the producing kernel leaves behind; 32768 when the
-//    producer is unknown) and the weight norm from a table wprep writes next to the tiles.  One vote per warp and tile; a warp that
-//    fails takes the EXACT path (the 4-instruction step, HH plane read in a second pass) for that tile, so the result is the
-//    reference's bits unconditionally.  profiles/microbench/tc_epilogue_rates.cu: 2.0 cycles per warp-step per SMSP for the fast
-//    step (2.5 with the range check) against 4.5 for the exact one.
+//    producer is unknown) and the weight norm from a table wprep writes next to the tiles.  One vote per warp and K-block (the
+//    group's three tiles); a warp that fails takes the EXACT step (HH plane read in a second pass) for that K-block, so the
+//    result is the reference's bits unconditionally.  profiles/microbench/tc_epilogue_rates.cu: 2.0 cycles per warp-step per
+//    SMSP for the fast step against 4.5 for the exact one.
+//  * The barrier ring (go / mma_done / rd_done, 12 slots = one K-block) is phase-safe: no barrier can complete a second phase
+//    before every waiter has tested the first (comments at the declarations).  -DY2_TC2_PROFILE builds deadlock-detecting waits
+//    and a per-role / per-tile cycle profile; -DY2_TC2_GRID=n runs n persistent CTAs (many items per CTA on small test shapes).
 #include "common.cuh"
 #include <cstdio>
 #include <cuda.h>            // CUtensorMap + enums only: the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
@@ -53,7 +50,7 @@ constexpr int kM = 128;             // output channels per CTA = TMEM lanes
 constexpr int kSteps = 7;           // chain steps per K-block: K = 32 = 7 x 4 channels | rounding row | 3 zero rows
 constexpr int kPx = 4;              // pixels per tile
 constexpr int kN = 32;              // MMA N = 8 step slots x 4 pixels (slot 7 unused)
-constexpr int kR = 12;              // tiles per K-block -> 48 pixels per CTA
+constexpr int kR = 12;              // tiles per K-block -> 48 pixels per pixel set
 constexpr int kPT = kPx * kR;
 #ifndef Y2_TC2_BUFS
 #define Y2_TC2_BUFS 5
@@ -72,7 +69,7 @@ constexpr int kGroups = 4;          // epilogue warpgroups; group kg takes the t
                                     //   slower than this unrolled form with compile-time barrier addresses, and 5 / 6 groups then recover 6 %
 constexpr int kTPG = kR / kGroups;  // tiles per group per K-block
 constexpr int kEpiWarps = 4 * kGroups;   // warps 0..: group kg = warp/4, TMEM lane quadrant = warp%4
-constexpr int kBuilders = 3;        // next warpgroup: builder bw takes the tile PAIRS (2j, 2j+1) with j = bw (mod 3); its fourth warp idles
+constexpr int kBuilders = 3;        // next warpgroup: builder bw takes the tile PAIRS (2j, 2j+1) with j = bw (mod 3); its fourth warp is the TMA producer
 constexpr int kIssuer = kEpiWarps + 4;   // last warpgroup: issuer iw takes the tiles r = iw (mod 4).  One warp issues one MMA per ~29 cycles
 constexpr int kIssuers = 4;         //   (profiles/microbench/umma_issue.cu) and pays ~100 cycles per mbarrier wait
 constexpr int kThreads = (kEpiWarps + 8) * 32;   // 768 threads, 80 registers at launch; setmaxnreg then moves registers
