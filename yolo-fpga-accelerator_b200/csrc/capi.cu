@@ -118,10 +118,14 @@ int run_conv_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, cons
 {
     cudaStream_t st = ctx->stream;
     const int so = Qa_in + Qw - Qa_out, sb = Qb - Qa_out;
+    // the C4 kernels' rounding group is 4 channels (or all of them when IFM <= 4); a context emulating a reference built with
+    // Tn = 8 / 16 (yolo2cuda_set_tile_params) groups 2 / 4 C4 words per step in the CUDA-core int16 kernel
+    const int gwords = (ctx->elem == 2 && (ctx->Tn == 8 || ctx->Tn == 16) && IFM > 4 && TN == (IFM < ctx->Tn ? IFM : ctx->Tn) && so <= 22) ? ctx->Tn / 4 : 1;
     bool fast = !ctx->force_generic && (K == 1 || K == 3) && S == 1 && Pad == K / 2 && Ow == Iw && Oh == Ih &&
-                (TN == 4 || (IFM <= TN && IFM <= 4));   // the C4 kernels' rounding group is 4 channels (or all of them when IFM <= 4)
+                (TN == 4 || (IFM <= TN && IFM <= 4) || gwords > 1);
     if (ctx->elem == 2) fast = fast && fast_shift_ok(so);
     ConvFastParams p{};
+    p.group_words = gwords;
     // a reference built with Tn = 32: one MMA K slice is one rounding group (csrc/conv_i16_tc32.cu)
     const bool tc32 = !fast && !ctx->force_generic && ctx->elem == 2 && ctx->Tn == 32 && TN == (IFM < 32 ? IFM : 32) && IFM > 4 &&
                       (K == 1 || K == 3) && S == 1 && Pad == K / 2 && Ow == Iw && Oh == Ih && so >= 8 && so <= 16;
@@ -162,7 +166,7 @@ int run_conv_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, cons
     int rc;
     if ((rc = ensure(ctx, ctx->s_c4in, c4_elems(IFM, Ih, Iw) * ctx->elem))) return rc;
     if ((rc = ensure(ctx, ctx->s_c4out, c4_elems(OFM, Oh, Ow) * ctx->elem))) return rc;
-    const bool tc = ctx->use_tc > 0 && ctx->elem == 2 && so >= 8 && so <= 22;   // (auto mode: single-frame calls stay on the CUDA cores)
+    const bool tc = ctx->use_tc > 0 && ctx->elem == 2 && so >= 8 && so <= 22 && gwords == 1;   // (auto mode: single-frame calls stay on the CUDA cores)
     if ((rc = ensure(ctx, ctx->s_wprep, tc ? wprep_tc2_bytes(IFM, OFM, K) : wprep_bytes(IFM, OFM, K, ctx->elem)))) return rc;
     launch_planar_to_c4(Input, ctx->s_c4in.p, 1, IFM, Ih, Iw, 0, 0, ctx->elem, st);
     if (tc) {
@@ -963,7 +967,8 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
             const int TM = l.d.n < ctx->Tm ? l.d.n : ctx->Tm, TN = l.d.c < ctx->Tn ? l.d.c : ctx->Tn;  // yolo2_model.cpp:307-308
             l.fast = !ctx->force_generic && (l.d.size == 1 || l.d.size == 3) && l.d.stride == 1 && l.d.pad == l.d.size / 2 &&
                      l.d.out_w == l.d.w && l.d.out_h == l.d.h && (e == 4 || fast_shift_ok(so)) &&
-                     (e == 4 || TN == 4 || l.d.c <= 4);   // int16: the C4 kernels' rounding group is 4 channels
+                     (e == 4 || TN == 4 || l.d.c <= 4 ||   // int16: the C4 kernels' rounding group is 4 channels, or 2 / 4 C4 words (Tn 8 / 16)
+                      ((ctx->Tn == 8 || ctx->Tn == 16) && so <= 22));
             l.tc32 = false;
             if (!l.fast && !ctx->force_generic && e == 2 && ctx->Tn == 32 && l.d.c > 4 && (l.d.size == 1 || l.d.size == 3) &&
                 l.d.stride == 1 && l.d.pad == l.d.size / 2 && l.d.out_w == l.d.w && l.d.out_h == l.d.h && so >= 8 && so <= 16) {
@@ -983,6 +988,10 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
             if (l.fast) {
                 ConvFastParams p{};
                 p.B = net->max_batch; p.H = l.d.h; p.W = l.d.w; p.G = ceil_div(l.d.c, 4); p.OFM = l.d.n;
+                // rounding group of 4 channels (reference default, or a layer with <= 4 input channels under any Tn): every int16 kernel;
+                // Tn = 8 / 16 builds: 2 / 4 C4 words per step in the CUDA-core kernel only (the tcgen05 kernels implement Tn = 4 and 32)
+                const bool group4 = e == 4 || TN == 4 || l.d.c <= 4;
+                p.group_words = group4 ? 1 : ctx->Tn / 4;
                 if (conv_fast_plan(p, l.d.size, e) == 0) l.fast = false;
                 else {
                     if (!l.w_dev && (rc = net_alloc(net, &l.w_dev, wprep_bytes(l.d.c, l.d.n, l.d.size, e)))) return rc;
@@ -995,14 +1004,14 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                     p.so = so > 30 ? 30 : so; p.sb = l.Qb - l.Qa_out; p.leaky = l.d.leaky;
                     l.cp = p;
                     // tensor-core path: wide layers only (a CTA covers 128 output channels)
-                    l.tc = ctx->use_tc > 0 && e == 2 && so >= 8 && so <= 22 && l.d.n >= ctx->tc_min_ofm;
+                    l.tc = ctx->use_tc > 0 && e == 2 && group4 && so >= 8 && so <= 22 && l.d.n >= ctx->tc_min_ofm;
                     // auto: the persistent tcgen05 kernel wherever its 128-channel tiles are at least 80 % full and the chain is deep
                     // enough to feed it (measured, profiles/r2_layer_table_int16_b128_persistent*.json: 5.1-5.6 T steps/s on every 3x3
                     // layer from 104 to 13 wide and 4.1-4.6 T on the 1x1 layers, against 2.6-3.8 T on the CUDA cores); layer 0 (3 input
                     // channels, 32 output channels) stays on the CUDA-core kernel.  Both paths are bit-exact, so mixing them is safe.
                     // (128-channel tiles, or 64-channel tiles x two pixel sets when those fill better: conv_i16_tc2.cu half_mode)
                     const bool fill128 = l.d.n * 5 >= ceil_div(l.d.n, 128) * 128 * 4, fill64 = l.d.n * 5 >= ceil_div(l.d.n, 64) * 64 * 4;
-                    if (ctx->use_tc < 0 && e == 2 && so >= 8 && so <= 22 && (fill128 || fill64) &&
+                    if (ctx->use_tc < 0 && e == 2 && group4 && so >= 8 && so <= 22 && (fill128 || fill64) &&
                         ((l.d.size == 3 && l.d.c >= 32) || (l.d.size == 1 && l.d.c >= 128)) &&
                         conv_i16_tc2_eligible(p, l.d.size, net->max_batch))
                         l.tc = true;

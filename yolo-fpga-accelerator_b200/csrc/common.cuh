@@ -63,6 +63,7 @@ struct ConvFastParams {
     int *xmax_out;         // device scalar the kernel atomicMax-es the largest |output| into
     unsigned long long *tc_stats;   // device [2]: warp-tiles through the fast / the exact path of the tcgen05 kernel (NULL = not counted)
     int tc_force_exact;    // tests: the tcgen05 kernel never takes the fast path
+    int group_words;       // C4 words per rounding group of the CUDA-core int16 kernel: 0 / 1 = Tn 4 (default), 2 = Tn 8, 4 = Tn 16
 };
 
 // ---- launchers (defined in the .cu files; all asynchronous on `st`) ---------------------------

@@ -74,9 +74,13 @@ constexpr int kThreads = 32 * kWM * kWS;
 
 // One CTA: a band of RB image rows (flattened over frames) x 16 output channels.
 // One thread: one row segment of TP pixels x 4 output channels = 4*TP saturating accumulators.
-template <int TP, int KS, bool SCALED>
+// NW = C4 words per ROUNDING GROUP: 1 for the reference's default Tn = 4; 2 / 4 emulate a reference built with
+// scripts/hw_params_gen.py --tn 8 / 16 (hls/core/params.hpp), whose round-and-saturate step covers 8 / 16 input channels: the
+// partial sums of the group's words are added up exactly (|sum x*w_lo| < 2^28, |sum x*w_hi| < 2^27) before the one step.
+template <int TP, int KS, bool SCALED, int NW = 1>
 __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFastParams p)
 {
+    static_assert(NW == 1 || (SCALED && TP <= 7), "wider rounding groups: scaled form, 7-pixel segments (register budget)");
     constexpr int K2 = KS * KS;
     constexpr int PAD = KS / 2;
     constexpr int XW = TP + KS - 1;
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
             long long base = round_shift64(b, p.sb);
             // |rs(P,so)| <= rb on this path, so clamping base+32768 to [-rb, 65535+rb] cannot change
             // clamp(base+32768+r, 0, 65535); it keeps the (scaled) state inside int32
-            const long long rb = (SCALED ? ((1LL << 25) >> k2) : (1LL << 26)) + 2;
+            const long long rb = (SCALED ? (((long long)NW << 25) >> k2) : (1LL << 26)) + 2;
             long long boff = base + 32768;
             if (boff > 65535 + rb) boff = 65535 + rb;
             if (boff < -rb) boff = -rb;
@@ -192,6 +196,48 @@ __global__ void __launch_bounds__(kThreads, 2) conv_i16_c4_kernel(const ConvFast
         const uint2 *wsm = sm + (st & 1) * stage_px + wm * kTMC;
         const uint2 *xs = sm + (st & 1) * stage_px + w_stage_px;
         const int ng = min(p.GS, p.G - st * p.GS);
+        if constexpr (NW > 1) {
+            // one step per (NW-word group, tap): partial sums over the group's words, then round + saturate once
+            for (int gg = 0; gg < ng; gg += NW) {
+#pragma unroll 1
+                for (int i = 0; i < KS; ++i) {
+                    int xo = xoff[0];
+#pragma unroll
+                    for (int t = 1; t < KS; ++t) xo = (i == t) ? xoff[t] : xo;
+#pragma unroll 1
+                    for (int j = 0; j < KS; ++j) {
+                        int plo[kTMC][TP], phi[kTMC][TP];
+#pragma unroll
+                        for (int c = 0; c < kTMC; ++c)
+#pragma unroll
+                            for (int q = 0; q < TP; ++q) { plo[c][q] = half; phi[c][q] = 0; }
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) {
+                            if (gg + w >= ng) break;            // the layer's last group may be narrower (uniform)
+                            const uint2 *xr = xs + (gg + w) * xrows * p.PW + xo + j;
+                            const uint2 *wg = wsm + (gg + w) * K2 * kCM + (i * KS + j) * kCM;
+                            uint2 xv[TP], wv[kTMC];
+#pragma unroll
+                            for (int q = 0; q < TP; ++q) xv[q] = xr[q];
+#pragma unroll
+                            for (int c = 0; c < kTMC; ++c) wv[c] = wg[c];
+#pragma unroll
+                            for (int c = 0; c < kTMC; ++c)
+#pragma unroll
+                                for (int q = 0; q < TP; ++q) {
+                                    plo[c][q] = dp2a_hi_su((int)xv[q].y, wv[c].x, dp2a_lo_su((int)xv[q].x, wv[c].x, plo[c][q]));
+                                    phi[c][q] = dp2a_hi_ss((int)xv[q].y, (int)wv[c].y, dp2a_lo_ss((int)xv[q].x, (int)wv[c].y, phi[c][q]));
+                                }
+                        }
+#pragma unroll
+                        for (int c = 0; c < kTMC; ++c)
+#pragma unroll
+                            for (int q = 0; q < TP; ++q)
+                                acc[c][q] = __vimin_s32_relu((acc[c][q] + (plo[c][q] >> 8) + phi[c][q]) & nmask, ubound);
+                    }
+                }
+            }
+        } else
         for (int gg = 0; gg < ng; ++gg) {
             const uint2 *xg = xs + gg * xrows * p.PW;
             const uint2 *wg = wsm + gg * K2 * kCM;
@@ -357,7 +403,8 @@ size_t conv_fast_plan(ConvFastParams &p, int ksize, int elem_bytes)
     // segment width: 13 when it tiles the row exactly (every YOLOv2-416 width) or nearly, else the better of 13 / 7;
     // the float kernel always uses 7 (a 16-byte pixel word doubles the register cost of a segment)
     int tp = 13;
-    if (elem_bytes == 4) tp = 7;
+    const int nw = (elem_bytes == 2 && p.group_words > 1) ? p.group_words : 1;
+    if (elem_bytes == 4 || nw > 1) tp = 7;
     else if (p.W % 13 != 0) {
         // 13-pixel segments reuse each weight over more pixels and give taller row bands (measured 3.6-3.8 T steps/s against
         // 2.3-3.6 for 7): keep them while the ragged last segment wastes < 10 % (every width of the 608 net: 38 ... 608)
@@ -365,7 +412,7 @@ size_t conv_fast_plan(ConvFastParams &p, int ksize, int elem_bytes)
         if (u13 < 0.9 && u7 > u13) tp = 7;
     }
     int sw = ceil_div(p.W, tp);
-    if (sw > kNS && tp == 7 && elem_bytes != 4 && ceil_div(p.W, 13) <= kNS) { tp = 13; sw = ceil_div(p.W, 13); }
+    if (sw > kNS && tp == 7 && elem_bytes != 4 && nw == 1 && ceil_div(p.W, 13) <= kNS) { tp = 13; sw = ceil_div(p.W, 13); }
     if (sw > kNS) return 0;
     p.TP = tp;
     p.SW = sw;
@@ -381,6 +428,7 @@ size_t conv_fast_plan(ConvFastParams &p, int ksize, int elem_bytes)
     if (gs < 1) gs = 1;
     if (gs > 8) gs = 8;
     if (gs > p.G) gs = p.G;
+    if (nw > 1) gs = gs < nw ? nw : gs / nw * nw;      // a rounding group never straddles two pipeline stages
     p.GS = gs;
     size_t smem = 2 * per_group * gs + 64 + tbl_bytes;
     if (smem > 200 * 1024) return 0;
@@ -399,6 +447,15 @@ static int launch_i16_variant(const ConvFastParams &p, size_t smem, cudaStream_t
     return 1;
 }
 
+template <int KS, int NW>
+static int launch_i16_group_variant(const ConvFastParams &p, size_t smem, cudaStream_t st)
+{
+    cudaFuncSetAttribute(conv_i16_c4_kernel<7, KS, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    dim3 grid(ceil_div(p.B * p.H, p.RB), ceil_div(p.OFM, kCM));
+    conv_i16_c4_kernel<7, KS, true, NW><<<grid, kThreads, smem, st>>>(p);
+    return 1;
+}
+
 int launch_conv_i16_fast(const ConvFastParams &p, int ksize, cudaStream_t st, const char **variant)
 {
     const int xrows = p.RB + ksize - 1 + 1;
@@ -406,6 +463,12 @@ int launch_conv_i16_fast(const ConvFastParams &p, int ksize, cudaStream_t st, co
                         (size_t)(p.RB + ksize - 1) * p.W * 8;  // + the copy table
     const int tp = p.TP;
     const bool scaled = p.so <= 22;
+    if (p.group_words > 1) {     // reference built with Tn = 8 / 16 (conv_fast_plan chose 7-pixel segments and GS % group_words == 0)
+        if (tp != 7 || !scaled || (p.group_words != 2 && p.group_words != 4) || p.GS % p.group_words) return -1;
+        if (variant) *variant = p.group_words == 2 ? (ksize == 3 ? "conv_i16_c4<7,3,tn8>" : "conv_i16_c4<7,1,tn8>") : (ksize == 3 ? "conv_i16_c4<7,3,tn16>" : "conv_i16_c4<7,1,tn16>");
+        if (ksize == 3) return p.group_words == 2 ? launch_i16_group_variant<3, 2>(p, smem, st) : launch_i16_group_variant<3, 4>(p, smem, st);
+        return p.group_words == 2 ? launch_i16_group_variant<1, 2>(p, smem, st) : launch_i16_group_variant<1, 4>(p, smem, st);
+    }
 #define Y2_VARIANT(TPV, KSV)                                                                                  \
     if (tp == TPV && ksize == KSV) {                                                                           \
         if (variant) *variant = scaled ? "conv_i16_c4<" #TPV "," #KSV ",scaled>" : "conv_i16_c4<" #TPV "," #KSV ",unscaled>"; \
