@@ -545,10 +545,11 @@ def test_tn32_tensor_core_conv_bit_exact(c, n, k, w, h, q, amp, oracle):
         acc.close()
 
 
-@pytest.mark.parametrize("tn", [8, 32])
+@pytest.mark.parametrize("tn", [8, 16, 32])
 def test_whole_net_rounding_group_variant(tn, oracle):
-    """a whole (thin) YOLOv2 through the network executor emulating a reference built with --tn 8 (generic kernel) and
-    --tn 32 (tensor-core kernel), every layer's ofm and the region tensor bit-exact to the oracle with the same tile parameters"""
+    """a whole (thin) YOLOv2 through the network executor emulating a reference built with --tn 8 / 16 (CUDA-core kernel with 2 / 4
+    C4 words per rounding step) and --tn 32 (tensor-core kernel), every layer's ofm and the region tensor bit-exact to the oracle
+    with the same tile parameters"""
     from yolo2_b200.accel import Accelerator
     net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 3, channel_div=8))
     pack = yw.synth_pack(net, "int16", seed=21, table="default", tn=tn)
@@ -566,6 +567,9 @@ def test_whole_net_rounding_group_variant(tn, oracle):
                 got = y.layer_output(i, f)
                 assert np.array_equal(valid(got, net.layers[i].out_w), valid(want, net.layers[i].out_w)), (tn, i)
             assert np.array_equal(region[f].view(np.uint32), want_region.view(np.uint32))
+        kernels = {y.layer_kernel(i) for i in range(len(net.layers))}
+        assert any(k.endswith({8: "tn8>", 16: "tn16>", 32: ">"}[tn]) and k.startswith({8: "conv_i16_c4<", 16: "conv_i16_c4<", 32: "conv_i16_tc32<"}[tn])
+                   for k in kernels), kernels
     finally:
         oracle.set_tile_params(4, 32)
         y.close()
