@@ -173,7 +173,7 @@ int yolo2cuda_net_get_layer_output(yolo2cuda_net *net, int layer, int frame, voi
 int yolo2cuda_net_region_q(const yolo2cuda_net *net);
 /* Kernels launched by one forward of `batch` frames (0 before the first forward). */
 uint64_t yolo2cuda_net_launches_per_forward(const yolo2cuda_net *net);
-/* Pass schedule of yolo2cuda_net_forward_host / _forward_images_host for batches larger than max_batch: the upload of the first
+/* Pass schedule of yolo2cuda_net_forward_host for batches larger than max_batch (forward_images_host runs its passes back to back): the upload of the first
  * pass is the only one that does not overlap compute, so such a batch starts with a short RAMP pass of `frames` frames followed by
  * passes of max_batch (-1 = default max(32, max_batch / 6); 0 = no ramp pass).  The results do not depend on the schedule. */
 int yolo2cuda_net_set_ramp_frames(yolo2cuda_net *net, int frames);

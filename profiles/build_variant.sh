@@ -5,6 +5,6 @@ name=$1; shift
 cd /root/repo/yolo-fpga-accelerator_b200
 mkdir -p lib/variants
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -c -o lib/variants/tc2_$name.o csrc/conv_i16_tc2.cu
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o lib/variants/libyolo2cuda_$name.so lib/conv_i16.o lib/variants/tc2_$name.o lib/conv_i16_tc32.o lib/conv_f32.o lib/bw_ops.o lib/capi.o lib/detect.o -cudart static
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o lib/variants/libyolo2cuda_$name.so lib/conv_i16.o lib/conv_i16_g1.o lib/variants/tc2_$name.o lib/conv_i16_tc32.o lib/conv_f32.o lib/bw_ops.o lib/capi.o lib/detect.o -cudart static
 rm lib/variants/tc2_$name.o
 echo built $name
