@@ -227,3 +227,20 @@ def test_glibc_exp_data_header_matches_this_libm(tmp_path):
     out = os.path.join(tmp_path, "h.h")
     subprocess.check_call([sys.executable, os.path.join(root, "yolo-fpga-accelerator_b200", "csrc", "gen_glibc_exp_data.py"), libm, out])
     assert open(out).read() == open(os.path.join(root, "yolo-fpga-accelerator_b200", "csrc", "glibc_exp_data.h")).read()
+
+
+def test_pass_size_model_follows_the_persistent_kernel():
+    """model.pass_efficiency mirrors the work-item arithmetic of the persistent tcgen05 kernel: for YOLOv2-416 on 148 SMs a multiple
+    of 21 frames is exactly four rounds of (48-pixel x 128-channel) items on the 13x13x1024 layers, so best_pass_size / best_ramp_size
+    pick multiples of 21 and the 364-frame passes of round 1 rate lower; the policy mirror names the HALF-mode and CUDA-core layers."""
+    from yolo2_b200.model import _tensor_core_tile, best_pass_size, best_ramp_size, pass_efficiency
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 80))
+    assert (21 * 169 + 47) // 48 * 8 == 4 * 148
+    b = best_pass_size(net, 128, 400)
+    assert b % 21 == 0 and b >= 357
+    assert best_ramp_size(net, b) % 21 == 0 and 32 <= best_ramp_size(net, b) <= b // 4
+    assert pass_efficiency(net, b) > 0.999 > pass_efficiency(net, 364) > 0.99
+    tiles = {i: _tensor_core_tile(l) for i, l in enumerate(net.layers) if l.type == ycfg.CONV}
+    assert tiles[0] is None                                        # 3 input channels: conv_i16_g1_kernel
+    assert [i for i, t in tiles.items() if t == (64, 96)] == [2, 5, 26]      # 64 output channels: HALF mode
+    assert all(t == (128, 48) for i, t in tiles.items() if i not in (0, 2, 5, 26))
