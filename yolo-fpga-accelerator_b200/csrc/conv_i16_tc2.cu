@@ -278,7 +278,10 @@ __device__ long long g_tc2_prof[32 * 8];
 // per-tile timeline of 48 consecutive tiles of CTA (1,0): [tile - 600][event]: 0 builder starts (slot's previous tile read out), 1 built,
 // 2 issuer passed go, 3 issued + committed, 4..7 epilogue warp q passed mma_done, 8..11 read out + released, 12..15 computed
 __device__ long long g_tc2_tl[48 * 16];
-#define PROF_TL(tile, ev) do { if (blockIdx.x == 1 && blockIdx.y == 0 && lane == 0 && (tile) >= 600 && (tile) < 648) g_tc2_tl[((tile) - 600) * 16 + (ev)] = clock64(); } while (0)
+#ifndef Y2_TC2_TL0
+#define Y2_TC2_TL0 600      // first tile of the 48-tile timeline window (global tile counter of CTA 1: -DY2_TC2_TL0=<nkb*12 - 24> straddles the first item boundary)
+#endif
+#define PROF_TL(tile, ev) do { if (blockIdx.x == 1 && blockIdx.y == 0 && lane == 0 && (tile) >= Y2_TC2_TL0 && (tile) < Y2_TC2_TL0 + 48) g_tc2_tl[((tile) - Y2_TC2_TL0) * 16 + (ev)] = clock64(); } while (0)
 #else
 #define PROF_TL(tile, ev)
 #define PROF_DECL
@@ -803,6 +806,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             // the quad stores the complete 8-byte word of pixel q: one STG.64 per tile instead of four scattered STG.U16, and the
             // quad's four words are one full 32-byte sector (the 2-byte stores cost 1.6 % of a forward: -DY2_TC2_NOSTORE experiment)
             {
+                PROF_ADD(4);
                 const long long *oo = outoff + (n & (kTabSlots - 1)) * kPTI + pset * kPT;
                 int16_t *om = p.out + (long long)(m >> 2) * p.HW * 4;          // the quad's C4 word plane (m >> 2 is the same for its four lanes)
                 const int cq = lane & 3;
@@ -826,6 +830,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
                         if (cq & 1) { v[0] = s0; v[2] = s1; } else { v[1] = s0; v[3] = s1; }
                     }
                     // v[c] = channel (m & ~3) + c of pixel cq
+                    PROF_ADD(5);
                     const long long off = oo[(kGroups * rr + kg) * kPx + cq];
                     if (off >= 0 && (m & ~3) < p.OFM) {                        // (a quad entirely beyond OFM has no word in the output tensor)
 #pragma unroll
@@ -838,7 +843,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc2_kernel(const Tc2Para
             }
             mt = mt_next;
             wn = wn_next;
-            PROF_ADD(5);                            // (profile build: slot 5 = the per-item output store + re-initialisation)
+            PROF_ADD(6);                            // (profile build: slot 5 = activation + quad transpose, slot 6 = table read + store)
         }
         PROF_END;
         if (p.xmax_out) {
@@ -1098,14 +1103,14 @@ int launch_conv_i16_tc2(const ConvFastParams &cp, int ksize, cudaStream_t st, co
             for (int i = 0; i < 8; ++i) fprintf(stderr, " %9lld", h[w * 8 + i]);
             fprintf(stderr, "\n");
         }
-        if (p.nkb * kR >= 648) {
+        if ((long long)p.nkb * kR * ((p.nitems + (int)grid.x - 1) / (int)grid.x) >= Y2_TC2_TL0 + 48) {
             long long tl[48 * 16];
             cudaMemcpyFromSymbol(tl, g_tc2_tl, sizeof(tl));
             fprintf(stderr, "tc2 timeline (CTA 1,0), cycles relative to the first event; per tile: build start | built | issuer awake | issued | epilogue awake x4 | read out x4 | computed x4\n");
             long long t0 = tl[0];
             for (int i = 0; i < 48 * 16; ++i) if (tl[i] && tl[i] < t0) t0 = tl[i];
             for (int t = 0; t < 48; ++t) {
-                fprintf(stderr, "  tile %3d (slot %2d buf %d):", 600 + t, (600 + t) % kR, (600 + t) % kBufs);
+                fprintf(stderr, "  tile %3d (slot %2d buf %d):", Y2_TC2_TL0 + t, (Y2_TC2_TL0 + t) % kR, (Y2_TC2_TL0 + t) % kBufs);
                 for (int e = 0; e < 16; ++e) fprintf(stderr, " %6lld", tl[t * 16 + e] - t0);
                 fprintf(stderr, "\n");
             }
