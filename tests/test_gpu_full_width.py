@@ -85,3 +85,35 @@ def test_full_width_fp32_per_layer():
     """BASELINE configs[1]: full-width COCO 416 fp32, per-layer ofm diff against the reference's float build <= 1e-4 relative."""
     net, kernels = _run_case(416, 80, 2, 2, "fp32", "default", [0, 1], pack_seed=4, tol=1e-4)
     assert any(k.startswith("conv_f32_c4") for k in kernels.values()), kernels
+
+
+@pytest.mark.parametrize("tn,min_tc", [(16, 18), (8, 16)])
+def test_full_width_rounding_group_variant(tn, min_tc, oracle):
+    """SURVEY.md 8f-4 at full width: the network executor emulating a reference built with --tn 16 / 8, default policy (the deep
+    layers on the tensor-core kernel with 2 / 4 rounding steps per MMA K slice, csrc/conv_i16_tc32.cu; the shallow ones on the
+    grouped CUDA-core kernel), three frames in one pass: every layer of the first and last frame and all region tensors bit-exact
+    to the oracle with the same tile parameters (itself pinned against the reference built with that Tn)."""
+    from yolo2_b200.accel import Accelerator
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 80))
+    pack = yw.synth_pack(net, "int16", seed=5, table="default", tn=tn)
+    frames = yw.synth_frames(net, 3, seed=7000)
+    acc = Accelerator(0, "int16")
+    acc.set_tile_params(tn, 32)
+    oracle.set_tile_params(tn, 32)
+    y = Yolo2Net(net, pack, max_batch=3, accel=acc)
+    y.set_debug_keep(True)
+    try:
+        region = y.forward(frames)
+        kernels = {i: y.layer_kernel(i) for i in range(len(net.layers))}
+        for f in (0, 1, 2):
+            want_region, dumps = oracle.net_forward(net, frames[f], pack, dump_layers=f != 1)
+            assert np.array_equal(region[f].view(np.uint32), want_region.reshape(region[f].shape).view(np.uint32)), (tn, f)
+            for i, want in (dumps or {}).items():
+                ow = net.layers[i].out_w
+                assert np.array_equal(valid(y.layer_output(i, f), ow), valid(want, ow)), (tn, f, i, kernels[i])
+        tc = [i for i, k in kernels.items() if k.startswith("conv_i16_tc32<") and k.endswith(f",tn{tn}>")]
+        assert len(tc) >= min_tc, kernels
+    finally:
+        oracle.set_tile_params(4, 32)
+        y.close()
+        acc.close()

@@ -545,11 +545,40 @@ def test_tn32_tensor_core_conv_bit_exact(c, n, k, w, h, q, amp, oracle):
         acc.close()
 
 
-@pytest.mark.parametrize("tn", [8, 16, 32])
-def test_whole_net_rounding_group_variant(tn, oracle):
+@pytest.mark.parametrize("tn", [8, 16])
+@pytest.mark.parametrize("c,n,k,w,h,q,amp", [
+    (64, 128, 3, 13, 13, (14, 10, 10, 10), 600), (32, 64, 3, 52, 39, (14, 10, 10, 10), 600), (256, 200, 3, 26, 26, (13, 9, 12, 7), 600),
+    (96, 40, 1, 19, 19, (10, 10, 7, 8), 3000), (37, 33, 3, 20, 11, (13, 9, 12, 7), 32767), (16, 130, 3, 21, 9, (4, 10, 6, 12), 32767),
+    (512, 256, 1, 26, 26, (15, 10, 9, 11), 600), (1024, 128, 3, 13, 13, (14, 10, 10, 10), 600), (72, 24, 1, 13, 13, (14, 10, 10, 10), 32767),
+    (200, 136, 3, 104, 7, (14, 10, 10, 10), 600)])
+def test_tn8_tn16_tensor_core_conv_bit_exact(tn, c, n, k, w, h, q, amp, oracle, monkeypatch):
+    """csrc/conv_i16_tc32.cu with TNW = 16 / 8: one MMA K slice holds two / four consecutive rounding steps as a block-diagonal
+    activation operand.  Same bits as the oracle with TN = tn (pinned against that reference build in tests/test_oracle_vs_ref.py):
+    saturation, ragged channel counts (last group short, slices that straddle two channel groups and two staging chunks, step slots
+    past the last step), partial pixel tiles and output-channel tiles, both kernel sizes."""
+    monkeypatch.setenv("YOLO2CUDA_TC", "2")
+    from yolo2_b200.accel import Accelerator
+    acc = Accelerator(0, "int16")
+    try:
+        acc.set_tile_params(tn, 32)
+        a, x, wr, b, _ = make_conv_case(c * n + k + tn, c, n, k, 1, w, h, 1, amp=amp, xamp=32767 if amp > 600 else 2000, tn=tn)
+        want = oracle_conv(oracle, a, x, wr, b, q)
+        got = accel_call(acc, a, x, wr, b, q)
+        if 8 <= q[0] + q[1] - q[2] <= 16:
+            assert acc.last_kernel.startswith("conv_i16_tc32<") and acc.last_kernel.endswith(f",tn{tn}>"), acc.last_kernel
+        assert np.array_equal(valid(got, w), valid(want, w))
+    finally:
+        acc.close()
+
+
+@pytest.mark.parametrize("tn,tc", [(8, ""), (16, ""), (32, ""), (8, "2"), (16, "2")])
+def test_whole_net_rounding_group_variant(tn, tc, oracle, monkeypatch):
     """a whole (thin) YOLOv2 through the network executor emulating a reference built with --tn 8 / 16 (CUDA-core kernel with 2 / 4
-    C4 words per rounding step) and --tn 32 (tensor-core kernel), every layer's ofm and the region tensor bit-exact to the oracle
-    with the same tile parameters"""
+    C4 words per rounding step, or - forced here with YOLO2CUDA_TC=2, by policy on deep layers - the tensor-core kernel with 4 / 2
+    steps per K slice) and --tn 32 (tensor-core kernel), every layer's ofm and the region tensor bit-exact to the oracle with the
+    same tile parameters"""
+    if tc:
+        monkeypatch.setenv("YOLO2CUDA_TC", tc)
     from yolo2_b200.accel import Accelerator
     net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 3, channel_div=8))
     pack = yw.synth_pack(net, "int16", seed=21, table="default", tn=tn)
@@ -568,8 +597,8 @@ def test_whole_net_rounding_group_variant(tn, oracle):
                 assert np.array_equal(valid(got, net.layers[i].out_w), valid(want, net.layers[i].out_w)), (tn, i)
             assert np.array_equal(region[f].view(np.uint32), want_region.view(np.uint32))
         kernels = {y.layer_kernel(i) for i in range(len(net.layers))}
-        assert any(k.endswith({8: "tn8>", 16: "tn16>", 32: ">"}[tn]) and k.startswith({8: "conv_i16_c4<", 16: "conv_i16_c4<", 32: "conv_i16_tc32<"}[tn])
-                   for k in kernels), kernels
+        assert any(k.endswith({8: "tn8>", 16: "tn16>", 32: ">"}[tn]) and
+                   k.startswith("conv_i16_tc32<" if (tc or tn == 32) else "conv_i16_c4<") for k in kernels), kernels
     finally:
         oracle.set_tile_params(4, 32)
         y.close()

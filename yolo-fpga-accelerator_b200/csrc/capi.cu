@@ -126,21 +126,24 @@ int run_conv_layer_dev(yolo2cuda_ctx *ctx, const void *Input, void *Output, cons
     if (ctx->elem == 2) fast = fast && fast_shift_ok(so);
     ConvFastParams p{};
     p.group_words = gwords;
-    // a reference built with Tn = 32: one MMA K slice is one rounding group (csrc/conv_i16_tc32.cu)
-    const bool tc32 = !fast && !ctx->force_generic && ctx->elem == 2 && ctx->Tn == 32 && TN == (IFM < 32 ? IFM : 32) && IFM > 4 &&
-                      (K == 1 || K == 3) && S == 1 && Pad == K / 2 && Ow == Iw && Oh == Ih && so >= 8 && so <= 16;
+    // a reference built with Tn = 32: one MMA K slice is one rounding group (csrc/conv_i16_tc32.cu); Tn = 16 / 8: two / four
+    // rounding groups per K slice (block-diagonal operand) - in this single-frame entry only when YOLO2CUDA_TC forces it, like the
+    // Tn = 4 tensor-core kernel (the network executor decides per layer)
+    const bool tcn_shape = !ctx->force_generic && ctx->elem == 2 && IFM > 4 && TN == (IFM < ctx->Tn ? IFM : ctx->Tn) && (K == 1 || K == 3) &&
+                           S == 1 && Pad == K / 2 && Ow == Iw && Oh == Ih && so >= 8 && so <= 16;
+    const bool tc32 = tcn_shape && ((ctx->Tn == 32 && !fast) || ((ctx->Tn == 16 || ctx->Tn == 8) && ctx->use_tc > 0));
     if (tc32) {
         int rc;
         if ((rc = ensure(ctx, ctx->s_c4in, c4_elems(IFM, Ih, Iw) * ctx->elem))) return rc;
         if ((rc = ensure(ctx, ctx->s_c4out, c4_elems(OFM, Oh, Ow) * ctx->elem))) return rc;
-        if ((rc = ensure(ctx, ctx->s_wprep, wprep_tc32_bytes(IFM, OFM, K)))) return rc;
+        if ((rc = ensure(ctx, ctx->s_wprep, wprep_tc32_bytes(IFM, OFM, K, ctx->Tn)))) return rc;
         launch_planar_to_c4(Input, ctx->s_c4in.p, 1, IFM, Ih, Iw, 0, 0, ctx->elem, st);
-        launch_wprep_tc32((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, st);
+        launch_wprep_tc32((const int16_t *)Weight, ctx->s_wprep.p, IFM, OFM, K, TM, TN, ctx->Tn, st);
         p.B = 1; p.H = Ih; p.W = Iw; p.G = ceil_div(IFM, 4); p.OFM = OFM;
         p.in = ctx->s_c4in.p; p.out = ctx->s_c4out.p; p.w = ctx->s_wprep.p; p.bias = Beta;
         p.in_frame_stride = 0; p.out_frame_stride = 0;
         p.so = so; p.sb = sb; p.leaky = IsNL;
-        if (launch_conv_i16_tc32(p, K, IFM, st, &ctx->last_kernel) > 0) {
+        if (launch_conv_i16_tc32(p, K, IFM, ctx->Tn, st, &ctx->last_kernel) > 0) {
             launch_c4_to_planar(ctx->s_c4out.p, Output, 1, OFM, Oh, Ow, 0, 0, ctx->elem, st);
             ctx->launches += 4;
             CUDA_OK(ctx, cudaGetLastError());
@@ -462,7 +465,7 @@ struct LayerPlan {
     void *w_dev = nullptr;         // device weight layout (fast path)
     void *w_tc = nullptr;          // tcgen05 operand tiles (tensor-core path)
     bool tc = false;
-    bool tc32 = false;             // Tn = 32 build: csrc/conv_i16_tc32.cu
+    bool tc32 = false;             // Tn = 32 / 16 / 8 build on the tensor cores: csrc/conv_i16_tc32.cu
     bool g1 = false;               // one input channel group (IFM <= 4), 3x3: csrc/conv_i16_g1.cu
     bool pool_fusable = false;     //   ... and the next layer is a 2x2 / stride-2 max-pool of even dims that only reads this layer
     bool fused_away = false;       // max-pool layer whose work the previous conv launch did (set per forward)
@@ -652,8 +655,8 @@ int forward_chunk(yolo2cuda_net *net, const float *frames_dev, int B, float *reg
             if (l.tc32) {
                 ConvFastParams p = l.cp;
                 p.B = B;
-                int n = launch_conv_i16_tc32(p, l.d.size, l.d.c, st, &l.variant);
-                if (n < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "layer %zu: Tn=32 tensor-core conv not eligible", i);
+                int n = launch_conv_i16_tc32(p, l.d.size, l.d.c, ctx->Tn, st, &l.variant);
+                if (n < 0) return fail(ctx, YOLO2CUDA_LAUNCH_ERROR, "layer %zu: Tn=%d tensor-core conv not eligible", i, ctx->Tn);
                 launches += n;
                 ctx->last_kernel = l.variant;
             } else if (l.fast) {
@@ -970,13 +973,27 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                      (e == 4 || TN == 4 || l.d.c <= 4 ||   // int16: the C4 kernels' rounding group is 4 channels, or 2 / 4 C4 words (Tn 8 / 16)
                       ((ctx->Tn == 8 || ctx->Tn == 16) && so <= 22));
             l.tc32 = false;
-            if (!l.fast && !ctx->force_generic && e == 2 && ctx->Tn == 32 && l.d.c > 4 && (l.d.size == 1 || l.d.size == 3) &&
-                l.d.stride == 1 && l.d.pad == l.d.size / 2 && l.d.out_w == l.d.w && l.d.out_h == l.d.h && so >= 8 && so <= 16) {
-                // reference built with Tn = 32: tensor-core kernel, one MMA K slice per rounding group
+            const bool tcn_shape = !ctx->force_generic && e == 2 && l.d.c > 4 && (l.d.size == 1 || l.d.size == 3) && l.d.stride == 1 &&
+                                   l.d.pad == l.d.size / 2 && l.d.out_w == l.d.w && l.d.out_h == l.d.h &&
+                                   conv_i16_tc32_eligible(l.d.w, l.d.size, so, ctx->Tn);
+            // Tn = 16 / 8 builds have a CUDA-core kernel too (2 / 4 C4 words per step, 3.0-3.4 T step equivalents/s on every layer);
+            // the tensor-core kernel is one work item per CTA (prologue + pipeline fill), so it takes the layers whose CTAs run
+            // enough K slices on full enough 128-channel tiles.  Measured per layer with the kernel forced on / off
+            // (profiles/r2_layer_table_int16_b32_tn{16,8}_{tc2,tc0}.json): it wins from (K slices x tile fill) = 8 for Tn = 16
+            // (256->128 1x1: 0.21 against 0.27 ms) and from 16 for Tn = 8 (512->256 1x1: 0.25 against 0.29 ms), and loses below
+            // (32->64 3x3 @208, Tn = 16: 3.1 against 2.0 ms).  YOLO2CUDA_TC=2: every eligible layer, =0: none.
+            bool tcn = false;
+            if (tcn_shape && (ctx->Tn == 16 || ctx->Tn == 8) && l.fast && ctx->use_tc != 0) {
+                const int slices = conv_i16_tc32_slices(l.d.c, l.d.size, ctx->Tn);
+                tcn = ctx->use_tc > 0 || (long long)slices * l.d.n >= (long long)(ctx->Tn == 16 ? 8 : 16) * ceil_div(l.d.n, 128) * 128;
+            }
+            if (tcn_shape && ((!l.fast && ctx->Tn == 32) || tcn)) {
+                // reference built with Tn = 32 / 16 / 8: tensor-core kernel, one MMA K slice per 1 / 2 / 4 rounding groups
+                l.fast = false;
                 ConvFastParams p{};
                 p.B = net->max_batch; p.H = l.d.h; p.W = l.d.w; p.G = ceil_div(l.d.c, 4); p.OFM = l.d.n;
-                if (!l.w_tc && (rc = net_alloc(net, &l.w_tc, wprep_tc32_bytes(l.d.c, l.d.n, l.d.size)))) return rc;
-                launch_wprep_tc32((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, st);
+                if (!l.w_tc && (rc = net_alloc(net, &l.w_tc, wprep_tc32_bytes(l.d.c, l.d.n, l.d.size, ctx->Tn)))) return rc;
+                launch_wprep_tc32((const int16_t *)net->d_wblob + l.w_off, l.w_tc, l.d.c, l.d.n, l.d.size, TM, TN, ctx->Tn, st);
                 ctx->launches += 1;
                 p.in = l.in.base; p.out = l.out.base; p.w = l.w_tc;
                 p.bias = (char *)net->d_bblob + l.b_off * e;

@@ -129,8 +129,10 @@ size_t wprep_tc2_bytes(int ifm, int ofm, int ksize);
 void launch_wprep_tc2(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, int so, cudaStream_t st);
 int launch_conv_i16_tc2(const ConvFastParams &p, int ksize, cudaStream_t st, const char **variant);
 bool conv_i16_tc2_eligible(const ConvFastParams &p, int ksize, int frames);   // shape / alignment rules of the launcher, without launching
-// tensor-core conv for a reference built with rounding group Tn = 32 (one MMA K slice = one step), csrc/conv_i16_tc32.cu
-size_t wprep_tc32_bytes(int ifm, int ofm, int ksize);
-void launch_wprep_tc32(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, cudaStream_t st);
-int launch_conv_i16_tc32(const ConvFastParams &p, int ksize, int ifm, cudaStream_t st, const char **variant);
+// tensor-core conv for a reference built with rounding group tn = 32, 16 or 8 (one MMA K slice = 32 / tn chain steps), csrc/conv_i16_tc32.cu
+size_t wprep_tc32_bytes(int ifm, int ofm, int ksize, int tn);
+void launch_wprep_tc32(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, int tn, cudaStream_t st);
+int launch_conv_i16_tc32(const ConvFastParams &p, int ksize, int ifm, int tn, cudaStream_t st, const char **variant);
+int conv_i16_tc32_slices(int ifm, int ksize, int tn);
+bool conv_i16_tc32_eligible(int W, int ksize, int so, int tn);   // shape rules of the launcher, without launching
 }  // namespace y2

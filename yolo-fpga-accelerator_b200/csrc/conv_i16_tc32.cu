@@ -1,5 +1,10 @@
-// INT16 convolution on the tensor cores for a reference BUILT with rounding group Tn = 32
-// (scripts/hw_params_gen.py --tn 32), bit-exact to that build.
+// INT16 convolution on the tensor cores for a reference BUILT with rounding group Tn = 32, 16 or 8
+// (scripts/hw_params_gen.py --tn 32 / 16 / 8), bit-exact to that build.  The text below describes Tn = 32; the
+// template parameter TNW generalises it: a K = 32 slice of the MMA holds S = 32 / TNW consecutive chain steps as a block-diagonal
+// activation operand (column (step s', pixel) is non-zero only in K rows TNW*s' .. TNW*s' + TNW - 1, the weights of step s' sit in
+// the same K rows of the A tile), a tile is TNW pixels x S steps (N = 32 columns, column = s' * TNW + pixel), a CTA owns 3 * TNW
+// consecutive pixels, and the epilogue applies a tile's S steps to its TNW accumulators in chain order.  Step slots past the
+// layer's last step carry zero operands: d = (0 + half) >> so = 0, a no-op on the already saturated accumulator.
 //
 // With Tn = 32 one step of the reference's chain (hls/core/core_compute.cpp:65-120) is
 //   acc = clamp16(acc + ((P + half) >> so)),  P = sum_{t<32} w[m][32g+t][tap] * x[32g+t][pixel+tap],
@@ -26,7 +31,7 @@ namespace {
 constexpr int kM = 128;             // output channels per CTA = TMEM lanes
 constexpr int kN = 32;              // pixels per tile = MMA N
 constexpr int kR = 3;               // tiles per step -> 96 pixels per CTA; tile r <-> epilogue group r, builder r, issuer r
-constexpr int kPT = kN * kR;
+constexpr int kPT = kN * kR;        // pixels per CTA for Tn = 32 (the largest: table sizes); a TNW variant owns kR * TNW pixels
 constexpr int kBufs = 5;            // TMEM accumulator buffers: HH | M | LL, 32 columns each
 constexpr int kBufCols = 3 * kN;
 constexpr int kRing = 12;           // activation tile ring (hi 1 KB | lo 1 KB) and barrier ring: 4 steps x 3 tiles
@@ -149,7 +154,8 @@ struct Tc32Params {
     int B, H, W, G, OFM;      // G = C4 groups of the input
     long long in_frame_stride, out_frame_stride;  // elements
     int sb, leaky;
-    int nsteps;               // ceil(IFM/32) * K*K
+    int nsteps;               // chain steps per output: ceil(IFM/Tn) * K*K
+    int nslices;              // MMA K slices: ceil(nsteps / (32/Tn))
     int ctab_cap;             // entries reserved for the activation copy table
     int PW, rows_max, gs_shift;  // staging: smem row pitch (pixels), band rows incl. halo + zero row, log2(C4 groups per chunk) >= 3
 };
@@ -162,11 +168,15 @@ __device__ __forceinline__ int tc32_step(int acc, int hh, int mm, int ll)
     return __viaddmin_s32_relu(acc, d, 65535);
 }
 
-template <int KS, int SO>
+template <int KS, int SO, int TNW>
 __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Params p)
 {
     constexpr int K2 = KS * KS;
     constexpr int PAD = KS / 2;
+    constexpr int S = 32 / TNW;         // chain steps per K slice
+    constexpr int PPT = kN / S;         // pixels per tile (= TNW)
+    constexpr int kPTv = PPT * kR;      // pixels per CTA
+    constexpr int GW = TNW / 4;         // C4 words per rounding group
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sW = smem;                                    // kWRing x 8 KB
     unsigned char *sB = sW + kWRing * kWBytes;                   // kRing x (hi 1 KB | lo 1 KB)
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long npix = (long long)p.B * p.H * p.W;
-    const long long pix0 = (long long)blockIdx.x * kPT;
+    const long long pix0 = (long long)blockIdx.x * kPTv;
     const int mtile = blockIdx.y;
     const int zero_slot = p.rows_max - 1;
     const int GS = 1 << p.gs_shift;
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int q = tid; q < kPT; q += kThreads) {
+    for (int q = tid; q < kPTv; q += kThreads) {
         long long gp = pix0 + q;
         int valid = gp < npix;
         long long grow = valid ? gp / p.W : row_first;
@@ -219,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
     // are copied (a CTA's pixels are consecutive, so on wide images it touches a fraction of each row), and the loader walks a
     // precomputed (source, destination) list instead of doing index arithmetic per element.
     if (tid == 0) {
-        const long long pix_last = (pix0 + kPT < npix ? pix0 + kPT : npix) - 1;
+        const long long pix_last = (pix0 + kPTv < npix ? pix0 + kPTv : npix) - 1;
         const long long row_last = pix_last / p.W;
         const int nrow_cta = (int)(row_last - row_first) + 1;
         const int x_first = (int)(pix0 - row_first * p.W), x_last = (int)(pix_last - row_last * p.W);
@@ -270,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
                 unsigned elected;
                 asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
                 int slot = iw, sph = 0, tb = iw;                 // ring slot it % 12 + its phase parity, TMEM buffer it % 5 (it = 3 s + iw)
-                for (int s = 0; s < p.nsteps; ++s) {
+                for (int s = 0; s < p.nslices; ++s) {
                     const int ws = s % kWRing;
                     mbar_wait(&w_full[ws], (s / kWRing) & 1);
                     mbar_wait(&go[slot], sph);
@@ -295,8 +305,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
         } else if (warp == kLoader) {
             // ===== weight ring: one 8 KB bulk copy per step =====
             if (lane == 0) {
-                const unsigned char *src = p.w + (size_t)mtile * p.nsteps * kWBytes;
-                for (int s = 0; s < p.nsteps; ++s) {
+                const unsigned char *src = p.w + (size_t)mtile * p.nslices * kWBytes;
+                for (int s = 0; s < p.nslices; ++s) {
                     const int ws = s % kWRing;
                     if (s >= kWRing) mbar_wait(&w_empty[ws], ((s / kWRing) - 1) & 1);
                     mbar_expect_tx(&w_full[ws], kWBytes);
@@ -304,62 +314,86 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
                 }
             }
         } else {
-            // ===== three builder warps: stage activations (cp.async); lane = one pixel of tile bw, it gathers the 32 channels of the
-            // step's group (eight C4 words) and writes the hi / lo byte planes of the B operand (row = pixel, K = channel) =====
+            // ===== three builder warps: stage activations (cp.async); lane = one COLUMN of tile bw = (step slot sp, pixel): it gathers
+            // the TNW channels of its step's rounding group (TNW/4 C4 words) at its pixel + tap and writes the hi / lo byte planes of
+            // its B-operand row (row = column, K = 32 bytes: zero outside the K rows TNW*sp .. TNW*sp + TNW - 1) =====
             const int bw = warp - kBuilder;
-            const int bt = bw * 32 + lane;              // 0..95 = the CTA pixel this lane owns
+            const int bi = bw * 32 + lane;              // builder thread index (staging)
+            const int sp = lane / PPT;                  // step slot of this lane's column within a K slice
+            const int bt = bw * PPT + (lane % PPT);     // the CTA pixel this lane owns
             constexpr int kBT = kR * 32;
-            const int nrows = p.rows_max - 1;           // staged band rows (the last slot is the all-zero row)
             const int nchunks = (p.G + GS - 1) >> p.gs_shift;
             auto stage_chunk = [&](int c) {
                 uint2 *dst = sX + (c & 1) * chunk_px;
                 const int g0 = c << p.gs_shift, ng = min(GS, p.G - g0);
                 const int per_group = rowinfo[2 * (p.rows_max - 1) + 1];
                 const long long plane = (long long)p.H * p.W;
-                for (int idx = bt; idx < ng * per_group; idx += kBT) {
+                for (int idx = bi; idx < ng * per_group; idx += kBT) {
                     const int gg = idx / per_group;
                     const int2 e = ctab[idx - gg * per_group];
                     cp_async8(dst + gg * p.rows_max * p.PW + e.y, p.in + (g0 + gg) * plane + e.x);
                 }
                 asm volatile("cp.async.commit_group;");
             };
-            const int r0 = operand_off(lane, 0), r1 = operand_off(lane, 16);   // this pixel's two 16-byte K chunks
-            int pxo[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) pxo[i] = pxtab[bt * 4 + i];
+            const int r0 = operand_off(lane, 0), r1 = operand_off(lane, 16);   // this column's two 16-byte K chunks
+            const int pxo0 = pxtab[bt * 4 + 0], pxo1 = pxtab[bt * 4 + 1], pxo2 = pxtab[bt * 4 + 2];
             stage_chunk(0);
             int staged = 0, ready = -1;
             int slot = bw, sph = 0;
-            for (int s = 0; s < p.nsteps; ++s) {
-                const int g32 = s / K2, tap = s - g32 * K2;
-                const int ti = tap / KS, tj = tap - ti * KS;
-                const int c_need = (8 * g32) >> p.gs_shift;      // the chunk holding this step's eight C4 groups
-                if (staged + 1 < nchunks && staged <= c_need) {
-                    bar_sync_named(1, kBT);             // every builder is past the steps of chunk staged-1
+            for (int sl = 0; sl < p.nslices; ++sl) {
+                // the chunks holding the C4 words of this slice's first and last step (warp-uniform; a slice spans at most two)
+                const int st_lo = sl * S, st_hi = min(st_lo + S, p.nsteps) - 1;
+                const int c_lo = ((st_lo / K2) * GW) >> p.gs_shift, c_hi = ((st_hi / K2) * GW) >> p.gs_shift;
+                if (staged + 1 < nchunks && staged <= c_lo) {
+                    bar_sync_named(1, kBT);             // every builder is past the slices that read chunk staged-1
                     stage_chunk(staged + 1);
                     ++staged;
                 }
-                if (ready < c_need) {
-                    if (staged > c_need) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                if (ready < c_hi) {
+                    if (staged > c_hi) asm volatile("cp.async.wait_group 1;" ::: "memory");
                     else asm volatile("cp.async.wait_group 0;" ::: "memory");
                     bar_sync_named(1, kBT);             // all builder warps see each other's copies
-                    ready = c_need;
+                    ready = c_hi;
                 }
-                if (s >= kRing / kR) mbar_wait(&mma_done[slot], sph ^ 1);   // the MMAs of the previous tile in this slot have read it
-                const uint2 *xs = sX + (c_need & 1) * chunk_px + ((8 * g32) & (GS - 1)) * p.rows_max * p.PW + pxo[ti] + tj;
-                unsigned hi[8], lo[8];
+                if (sl >= kRing / kR) mbar_wait(&mma_done[slot], sph ^ 1);   // the MMAs of the previous tile in this slot have read it
+                const int step = st_lo + sp;
+                unsigned hi[GW], lo[GW];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint2 x = make_uint2(0u, 0u);
-                    if (8 * g32 + j < p.G) x = xs[j * p.rows_max * p.PW];
-                    hi[j] = __byte_perm(x.x, x.y, 0x7531);
-                    lo[j] = __byte_perm(x.x, x.y, 0x6420);
+                for (int j = 0; j < GW; ++j) hi[j] = lo[j] = 0u;
+                if (step < p.nsteps) {
+                    const int g = step / K2, tap = step - g * K2;
+                    const int ti = tap / KS, tj = tap - ti * KS;
+                    const int w0 = g * GW;                           // first C4 word of the rounding group
+                    const uint2 *xs = sX + ((w0 >> p.gs_shift) & 1) * chunk_px + (w0 & (GS - 1)) * p.rows_max * p.PW +
+                                      (ti == 0 ? pxo0 : ti == 1 ? pxo1 : pxo2) + tj;
+#pragma unroll
+                    for (int j = 0; j < GW; ++j) {
+                        uint2 x = make_uint2(0u, 0u);
+                        if (w0 + j < p.G) x = xs[j * p.rows_max * p.PW];
+                        hi[j] = __byte_perm(x.x, x.y, 0x7531);
+                        lo[j] = __byte_perm(x.x, x.y, 0x6420);
+                    }
+                }
+                uint4 h0, h1, l0, l1;                                // K bytes 0..15 and 16..31 of the row, per plane
+                const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                if constexpr (TNW == 32) {
+                    h0 = make_uint4(hi[0], hi[1], hi[2], hi[3]); h1 = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    l0 = make_uint4(lo[0], lo[1], lo[2], lo[3]); l1 = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                } else if constexpr (TNW == 16) {
+                    const uint4 hv = make_uint4(hi[0], hi[1], hi[2], hi[3]), lv = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    h0 = sp == 0 ? hv : z4; h1 = sp == 0 ? z4 : hv;
+                    l0 = sp == 0 ? lv : z4; l1 = sp == 0 ? z4 : lv;
+                } else {
+                    const uint4 hv = (sp & 1) ? make_uint4(0u, 0u, hi[0], hi[1]) : make_uint4(hi[0], hi[1], 0u, 0u);
+                    const uint4 lv = (sp & 1) ? make_uint4(0u, 0u, lo[0], lo[1]) : make_uint4(lo[0], lo[1], 0u, 0u);
+                    h0 = sp < 2 ? hv : z4; h1 = sp < 2 ? z4 : hv;
+                    l0 = sp < 2 ? lv : z4; l1 = sp < 2 ? z4 : lv;
                 }
                 unsigned char *bh = sB + (slot * 2) * kBBytes;
-                *reinterpret_cast<uint4 *>(bh + r0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4 *>(bh + r1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                *reinterpret_cast<uint4 *>(bh + kBBytes + r0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<uint4 *>(bh + kBBytes + r1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                *reinterpret_cast<uint4 *>(bh + r0) = h0;
+                *reinterpret_cast<uint4 *>(bh + r1) = h1;
+                *reinterpret_cast<uint4 *>(bh + kBBytes + r0) = l0;
+                *reinterpret_cast<uint4 *>(bh + kBBytes + r1) = l1;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&go[slot]);
@@ -373,29 +407,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
         const int q4 = warp & 3, kg = warp >> 2;
         const int m = mtile * kM + q4 * 32 + lane;
         const unsigned lane_base = tmem + ((unsigned)(q4 * 32) << 16);
-        int U[kN];
+        int U[PPT];                                 // acc + 32768 of the tile's PPT pixels; column n = step slot * PPT + pixel
         {
             long long bv = (m < p.OFM) ? (long long)p.bias[m] : 0;
             long long bs = round_shift64(bv, p.sb);
-            const long long rb = (1LL << (38 - SO)) + 2;      // |(P + half) >> so| <= 2^(38-so) for 32 products: clamping the bias term there cannot change clamp16(bias + r)
+            const long long rb = (1LL << (38 - SO)) + 2;      // |(P + half) >> so| <= 2^(38-so) for <= 32 products: clamping the bias term there cannot change clamp16(bias + r)
             long long boff = bs + 32768;
             if (boff > 65535 + rb) boff = 65535 + rb;
             if (boff < -rb) boff = -rb;
 #pragma unroll
-            for (int j = 0; j < kN; ++j) U[j] = (int)boff;
+            for (int j = 0; j < PPT; ++j) U[j] = (int)boff;
         }
         int slot = kg, sph = 0, tb = kg;
-        for (int s = 0; s < p.nsteps; ++s) {
+        for (int s = 0; s < p.nslices; ++s) {
             mbar_wait(&mma_done[slot], sph);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const unsigned base = lane_base + tb * kBufCols;
             int hh[16], mm[16], ll[16];
-            tmem_ld16(base, hh); tmem_ld16(base + kN, mm); tmem_ld16(base + 2 * kN, ll);          // pixels 0-15
+            tmem_ld16(base, hh); tmem_ld16(base + kN, mm); tmem_ld16(base + 2 * kN, ll);          // columns 0-15
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             reg_fence16(hh); reg_fence16(mm); reg_fence16(ll);
 #pragma unroll
-            for (int n = 0; n < 16; ++n) U[n] = tc32_step<SO>(U[n], hh[n], mm[n], ll[n]);
-            tmem_ld16(base + 16, hh); tmem_ld16(base + kN + 16, mm); tmem_ld16(base + 2 * kN + 16, ll);   // pixels 16-31
+            for (int n = 0; n < 16; ++n) U[n % PPT] = tc32_step<SO>(U[n % PPT], hh[n], mm[n], ll[n]);     // (unrolled in column order = chain order per pixel)
+            tmem_ld16(base + 16, hh); tmem_ld16(base + kN + 16, mm); tmem_ld16(base + 2 * kN + 16, ll);   // columns 16-31
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             reg_fence16(hh); reg_fence16(mm); reg_fence16(ll);
             // the whole tile has been read: hand the TMEM buffer to tile it+5
@@ -403,15 +437,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
             __syncwarp();
             if (lane == 0) mbar_arrive(&go[slot + kBufs < kRing ? slot + kBufs : slot + kBufs - kRing]);
 #pragma unroll
-            for (int n = 0; n < 16; ++n) U[16 + n] = tc32_step<SO>(U[16 + n], hh[n], mm[n], ll[n]);
+            for (int n = 0; n < 16; ++n) U[(16 + n) % PPT] = tc32_step<SO>(U[(16 + n) % PPT], hh[n], mm[n], ll[n]);
             slot += kR;
             if (slot >= kRing) { slot -= kRing; sph ^= 1; }
             tb = tb >= kBufs - kR ? tb - (kBufs - kR) : tb + kR;
         }
         if (m < p.OFM) {
 #pragma unroll
-            for (int j = 0; j < kN; ++j) {
-                const long long gp = pix0 + kg * kN + j;
+            for (int j = 0; j < PPT; ++j) {
+                const long long gp = pix0 + kg * PPT + j;
                 if (gp >= npix) continue;
                 const long long grow = gp / p.W;
                 const int x = (int)(gp - grow * p.W);
@@ -428,10 +462,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
     if (warp == kIssuer) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
-// Weight tiles from one layer of the reference's reorganised blob (addressed with the build's TM / TN = 32):
-// [mtile][step = (32-channel group, tap)][plane hi | lo][canonical 128 rows x 32 K-bytes].
+// Weight tiles from one layer of the reference's reorganised blob (addressed with the build's TM / TN):
+// [mtile][K slice][plane hi | lo][canonical 128 rows x 32 K-bytes]; K byte k of slice sl is channel k % tn of the rounding group of
+// chain step sl * (32 / tn) + k / tn (step = (group, tap)); step slots past the last step are zero.
 __global__ void wprep_tc32_kernel(const int16_t *__restrict__ blob, unsigned char *__restrict__ dst, int ifm, int ofm, int ksize,
-                                  int TM, int TN, int nsteps, long long total)
+                                  int TM, int TN, int tn, int nsteps, int nslices, long long total)
 {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -439,35 +474,36 @@ __global__ void wprep_tc32_kernel(const int16_t *__restrict__ blob, unsigned cha
     int k = idx & 31;
     long long r = idx >> 5;
     int ml = r % kM; r /= kM;
-    int s = r % nsteps;
-    int mtile = r / nsteps;
+    int sl = r % nslices;
+    int mtile = r / nslices;
     int m = mtile * kM + ml;
-    int g32 = s / k2, tap = s - g32 * k2, c = g32 * 32 + k;
+    int step = sl * (32 / tn) + k / tn;
+    int g = step / k2, tap = step - g * k2, c = g * tn + k % tn;
     int hi = 0, lo = 0;
-    if (m < ofm && c < ifm) {
+    if (m < ofm && c < ifm && step < nsteps) {
         int w = blob[reorg_woff(m, c, tap, ifm, ofm, k2, TM, TN)];
         hi = (w >> 8) & 0xff;
         lo = w & 0xff;
     }
-    unsigned char *tile = dst + ((size_t)mtile * nsteps + s) * kWBytes;
+    unsigned char *tile = dst + ((size_t)mtile * nslices + sl) * kWBytes;
     tile[operand_off(ml, k)] = (unsigned char)hi;
     tile[kM * 32 + operand_off(ml, k)] = (unsigned char)lo;
 }
 
-template <int KS, int SO>
+template <int KS, int SO, int TNW>
 void launch_one(const Tc32Params &p, dim3 grid, size_t smem, cudaStream_t st)
 {
     // set on every launch (a microsecond): the attribute is per device and a host may drive several GPUs from several threads,
     // so a cached "already configured" flag would be a data race for nothing
-    cudaFuncSetAttribute(conv_i16_tc32_kernel<KS, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    conv_i16_tc32_kernel<KS, SO><<<grid, kThreads, smem, st>>>(p);
+    cudaFuncSetAttribute(conv_i16_tc32_kernel<KS, SO, TNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    conv_i16_tc32_kernel<KS, SO, TNW><<<grid, kThreads, smem, st>>>(p);
 }
 
-template <int KS>
+template <int KS, int TNW>
 bool dispatch_so(const Tc32Params &p, int so, dim3 grid, size_t smem, cudaStream_t st)
 {
     switch (so) {
-#define Y2_TC32_CASE(S) case S: launch_one<KS, S>(p, grid, smem, st); return true;
+#define Y2_TC32_CASE(S) case S: launch_one<KS, S, TNW>(p, grid, smem, st); return true;
         Y2_TC32_CASE(8) Y2_TC32_CASE(9) Y2_TC32_CASE(10) Y2_TC32_CASE(11) Y2_TC32_CASE(12) Y2_TC32_CASE(13) Y2_TC32_CASE(14)
         Y2_TC32_CASE(15) Y2_TC32_CASE(16)
 #undef Y2_TC32_CASE
@@ -475,48 +511,89 @@ bool dispatch_so(const Tc32Params &p, int so, dim3 grid, size_t smem, cudaStream
     }
 }
 
+template <int KS>
+bool dispatch_tn(const Tc32Params &p, int so, int tn, dim3 grid, size_t smem, cudaStream_t st)
+{
+    switch (tn) {
+    case 32: return dispatch_so<KS, 32>(p, so, grid, smem, st);
+    case 16: return dispatch_so<KS, 16>(p, so, grid, smem, st);
+    case 8: return dispatch_so<KS, 8>(p, so, grid, smem, st);
+    default: return false;
+    }
+}
+
+// staging geometry of one CTA (pt = 3 * tn consecutive pixels): false when the image is too wide for the shared-memory band
+bool tc32_plan(int W, int ksize, int tn, Tc32Params &p, size_t &smem)
+{
+    const int pt = kR * tn;
+    p.PW = W + ksize - 1;
+    p.rows_max = (pt - 1) / W + 2 + (ksize - 1) + 1;
+    if (p.rows_max > 30) return false;                  // rowinfo[] holds 32 staged rows
+    p.ctab_cap = (p.rows_max - 1) * W;
+    const size_t fixed = (size_t)kWRing * kWBytes + (size_t)kRing * 2 * kBBytes + 512 + kPT * 16 + 256 + (size_t)p.ctab_cap * 8;
+    const size_t per_group = (size_t)p.rows_max * p.PW * 8;
+    if (fixed + 2 * per_group * 8 > 200 * 1024) return false;   // a chunk holds whole rounding groups: eight C4 words for Tn = 32 (and
+                                                                 // the chunk arithmetic of the narrower groups assumes at least that)
+    int gs = (int)((200 * 1024 - fixed) / (2 * per_group));
+    int sh = 3;
+    while ((2 << sh) <= gs && (2 << sh) <= 16) ++sh;    // largest power of two <= min(gs, 16)
+    p.gs_shift = sh;
+    gs = 1 << sh;
+    smem = fixed + 2 * per_group * gs + 1024;
+    if (smem < 120 * 1024) smem = 120 * 1024;           // one CTA per SM: a CTA allocates all 512 TMEM columns
+    return true;
+}
+
+inline int tc32_slices(int ifm, int ksize, int tn) { return ceil_div(ceil_div(ifm, tn) * ksize * ksize, 32 / tn); }
+
 }  // namespace
 
-size_t wprep_tc32_bytes(int ifm, int ofm, int ksize)
+size_t wprep_tc32_bytes(int ifm, int ofm, int ksize, int tn)
 {
-    return (size_t)ceil_div(ofm, kM) * ceil_div(ifm, 32) * ksize * ksize * kWBytes;
+    return (size_t)ceil_div(ofm, kM) * tc32_slices(ifm, ksize, tn) * kWBytes;
 }
 
-void launch_wprep_tc32(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, cudaStream_t st)
+void launch_wprep_tc32(const int16_t *blob, void *dst, int ifm, int ofm, int ksize, int TM, int TN, int tn, cudaStream_t st)
 {
-    const int nsteps = ceil_div(ifm, 32) * ksize * ksize;
-    const long long total = (long long)ceil_div(ofm, kM) * nsteps * kM * 32;
-    wprep_tc32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(blob, (unsigned char *)dst, ifm, ofm, ksize, TM, TN, nsteps, total);
+    const int nsteps = ceil_div(ifm, tn) * ksize * ksize, nslices = tc32_slices(ifm, ksize, tn);
+    const long long total = (long long)ceil_div(ofm, kM) * nslices * kM * 32;
+    wprep_tc32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(blob, (unsigned char *)dst, ifm, ofm, ksize, TM, TN, tn, nsteps,
+                                                                      nslices, total);
 }
 
-// Returns 1 when launched, -1 when the shape/shift is not eligible.
-int launch_conv_i16_tc32(const ConvFastParams &cp, int ksize, int ifm, cudaStream_t st, const char **variant)
+// K slices per CTA of a layer (the policy in capi.cu weighs them against the one-item-per-CTA prologue)
+int conv_i16_tc32_slices(int ifm, int ksize, int tn) { return tc32_slices(ifm, ksize, tn); }
+
+// the launcher's shape rules without launching (plan time)
+bool conv_i16_tc32_eligible(int W, int ksize, int so, int tn)
 {
-    if ((ksize != 1 && ksize != 3) || cp.so < 8 || cp.so > 16) return -1;
+    if ((ksize != 1 && ksize != 3) || so < 8 || so > 16 || (tn != 32 && tn != 16 && tn != 8)) return false;
+    Tc32Params p{};
+    size_t smem;
+    return tc32_plan(W, ksize, tn, p, smem);
+}
+
+// Returns 1 when launched, -1 when the shape/shift is not eligible.  tn = the emulated build's rounding group (32, 16 or 8).
+int launch_conv_i16_tc32(const ConvFastParams &cp, int ksize, int ifm, int tn, cudaStream_t st, const char **variant)
+{
+    if ((ksize != 1 && ksize != 3) || cp.so < 8 || cp.so > 16 || (tn != 32 && tn != 16 && tn != 8)) return -1;
     Tc32Params p{};
     p.in = (const uint2 *)cp.in; p.out = (int16_t *)cp.out; p.w = (const unsigned char *)cp.w; p.bias = (const int16_t *)cp.bias;
     p.B = cp.B; p.H = cp.H; p.W = cp.W; p.G = cp.G; p.OFM = cp.OFM;
     p.in_frame_stride = cp.in_frame_stride; p.out_frame_stride = cp.out_frame_stride;
     p.sb = cp.sb; p.leaky = cp.leaky;
-    p.nsteps = ceil_div(ifm, 32) * ksize * ksize;
-    p.PW = cp.W + ksize - 1;
-    p.rows_max = (kPT - 1) / cp.W + 2 + (ksize - 1) + 1;
-    if (p.rows_max > 30) return -1;                     // rowinfo[] holds 32 staged rows
-    p.ctab_cap = (p.rows_max - 1) * cp.W;
-    const size_t fixed = (size_t)kWRing * kWBytes + (size_t)kRing * 2 * kBBytes + 512 + kPT * 16 + 256 + (size_t)p.ctab_cap * 8;
-    const size_t per_group = (size_t)p.rows_max * p.PW * 8;
-    int gs = (int)((200 * 1024 - fixed) / (2 * per_group));
-    if (gs < 8) return -1;                              // a chunk must hold the eight C4 groups of one 32-channel rounding group
-    int sh = 3;
-    while ((2 << sh) <= gs && (2 << sh) <= 16) ++sh;    // largest power of two <= min(gs, 16)
-    p.gs_shift = sh;
-    gs = 1 << sh;
-    size_t smem = fixed + 2 * per_group * gs + 1024;
-    if (smem < 120 * 1024) smem = 120 * 1024;           // one CTA per SM: a CTA allocates all 512 TMEM columns
-    dim3 grid((unsigned)(((long long)cp.B * cp.H * cp.W + kPT - 1) / kPT), ceil_div(cp.OFM, kM));
-    const bool ok = ksize == 3 ? dispatch_so<3>(p, cp.so, grid, smem, st) : dispatch_so<1>(p, cp.so, grid, smem, st);
+    p.nsteps = ceil_div(ifm, tn) * ksize * ksize;
+    p.nslices = tc32_slices(ifm, ksize, tn);
+    const int pt = kR * tn;                             // pixels per CTA: three tiles of tn pixels x 32 / tn step slots
+    size_t smem;
+    if (!tc32_plan(cp.W, ksize, tn, p, smem)) return -1;
+    dim3 grid((unsigned)(((long long)cp.B * cp.H * cp.W + pt - 1) / pt), ceil_div(cp.OFM, kM));
+    const bool ok = ksize == 3 ? dispatch_tn<3>(p, cp.so, tn, grid, smem, st) : dispatch_tn<1>(p, cp.so, tn, grid, smem, st);
     if (!ok) return -1;
-    if (variant) *variant = ksize == 3 ? "conv_i16_tc32<3>" : "conv_i16_tc32<1>";
+    if (variant)
+        *variant = tn == 32 ? (ksize == 3 ? "conv_i16_tc32<3>" : "conv_i16_tc32<1>")
+                 : tn == 16 ? (ksize == 3 ? "conv_i16_tc32<3,tn16>" : "conv_i16_tc32<1,tn16>")
+                            : (ksize == 3 ? "conv_i16_tc32<3,tn8>" : "conv_i16_tc32<1,tn8>");
     return 1;
 }
 
