@@ -23,6 +23,10 @@
 //  hides.  The barrier ring has 12 = 4 steps x 3 tiles slots: slot -> fixed tile index r, so every barrier's
 // consecutive phases are awaited by the same warp.
 #include "common.cuh"
+#ifdef Y2_TC32_PROFILE
+#include <cstdio>
+#include <cstring>
+#endif
 
 namespace y2 {
 
@@ -35,7 +39,27 @@ constexpr int kPT = kN * kR;        // pixels per CTA for Tn = 32 (the largest: 
 constexpr int kBufs = 5;            // TMEM accumulator buffers: HH | M | LL, 32 columns each
 constexpr int kBufCols = 3 * kN;
 constexpr int kRing = 12;           // activation tile ring (hi 1 KB | lo 1 KB) and barrier ring: 4 steps x 3 tiles
-constexpr int kWRing = 4;           // weight ring: one 8 KB step tile per slot (hi 4 KB | lo 4 KB, canonical K-major)
+#ifndef Y2_TC32_WRING
+#define Y2_TC32_WRING 4
+#endif
+constexpr int kWRing = Y2_TC32_WRING;   // weight ring: one 8 KB step tile per slot (hi 4 KB | lo 4 KB, canonical K-major)
+// experiment builds (profiles/build_variant_tc32.sh; wrong results, timing only): -DY2_TC32_EXP=1 no step arithmetic, =2 no TMEM
+// read-out (arithmetic on opaque registers), =3 no MMAs (the issuers only commit)
+#ifndef Y2_TC32_EXP
+#define Y2_TC32_EXP 0
+#endif
+// -DY2_TC32_PROFILE: per-tile timeline (clock64) of CTA (1,0), tiles Y2_TC32_TL0 .. +47 (tile = 3 * slice + r), printed by the launcher:
+// 0 builder passed mma_done (slot free) | 1 built + arrived | 2 issuer passed w_full | 3 issuer passed go | 4 issued + committed |
+// 5 epilogue (quadrant 0) passed mma_done | 6 first half read | 7 released | 8 computed | 9 loader passed w_empty | 10 loader issued
+#ifdef Y2_TC32_PROFILE
+#ifndef Y2_TC32_TL0
+#define Y2_TC32_TL0 300
+#endif
+__device__ long long g_tc32_tl[48 * 16];
+#define PROF_TL(tile, ev) do { if (blockIdx.x == 1 && blockIdx.y == 0 && lane == 0 && (tile) >= Y2_TC32_TL0 && (tile) < Y2_TC32_TL0 + 48) g_tc32_tl[((tile) - Y2_TC32_TL0) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define PROF_TL(tile, ev)
+#endif
 constexpr int kEpiWarps = 12;       // warps 0-11: group kg = warp/4, TMEM lane quadrant = warp%4
 constexpr int kBuilder = 12;        // warps 12-14
 constexpr int kLoader = 15;         // warp 15: weight ring
@@ -283,20 +307,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
                 for (int s = 0; s < p.nslices; ++s) {
                     const int ws = s % kWRing;
                     mbar_wait(&w_full[ws], (s / kWRing) & 1);
+                    PROF_TL(s * kR + iw, 2);
                     mbar_wait(&go[slot], sph);
+                    PROF_TL(s * kR + iw, 3);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     if (elected) {
                         const unsigned long long dAh = dA0 + ws * kAStep, dAl = dAh + kAPlane;
                         const unsigned long long dBh = dB0 + slot * kBStep, dBl = dBh + kBPlane;
                         const unsigned d0 = tmem + tb * kBufCols;
+#if Y2_TC32_EXP != 3
                         umma_i8_ss(d0, dAh, dBh, idesc_i8(1, 1), 0);            // HH
                         umma_i8_ss(d0 + kN, dAh, dBl, idesc_i8(1, 0), 0);       // M  = hi*lo
                         umma_i8_ss(d0 + kN, dAl, dBh, idesc_i8(0, 1), 1);       //    + lo*hi
                         umma_i8_ss(d0 + 2 * kN, dAl, dBl, idesc_i8(0, 0), 0);   // LL
+#endif
                         umma_commit(&mma_done[slot]);                           // epilogue (tile ready) and builder (slot free)
                         umma_commit(&w_empty[ws]);                              // this warp's reads of the step's weights are done
                     }
                     __syncwarp();
+                    PROF_TL(s * kR + iw, 4);
                     slot += kR;
                     if (slot >= kRing) { slot -= kRing; sph ^= 1; }
                     tb = tb >= kBufs - kR ? tb - (kBufs - kR) : tb + kR;
@@ -309,8 +338,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
                 for (int s = 0; s < p.nslices; ++s) {
                     const int ws = s % kWRing;
                     if (s >= kWRing) mbar_wait(&w_empty[ws], ((s / kWRing) - 1) & 1);
+                    PROF_TL(s * kR, 9);
                     mbar_expect_tx(&w_full[ws], kWBytes);
                     bulk_g2s(sW + ws * kWBytes, src + (size_t)s * kWBytes, kWBytes, &w_full[ws]);
+                    PROF_TL(s * kR, 10);
                 }
             }
         } else {
@@ -356,6 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
                     ready = c_hi;
                 }
                 if (sl >= kRing / kR) mbar_wait(&mma_done[slot], sph ^ 1);   // the MMAs of the previous tile in this slot have read it
+                PROF_TL(sl * kR + bw, 0);
                 const int step = st_lo + sp;
                 unsigned hi[GW], lo[GW];
 #pragma unroll
@@ -397,6 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&go[slot]);
+                PROF_TL(sl * kR + bw, 1);
                 slot += kR;
                 if (slot >= kRing) { slot -= kRing; sph ^= 1; }
             }
@@ -421,23 +454,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
         int slot = kg, sph = 0, tb = kg;
         for (int s = 0; s < p.nslices; ++s) {
             mbar_wait(&mma_done[slot], sph);
+            if (q4 == 0) PROF_TL(s * kR + kg, 5);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const unsigned base = lane_base + tb * kBufCols;
             int hh[16], mm[16], ll[16];
+#if Y2_TC32_EXP == 2
+#pragma unroll
+            for (int n = 0; n < 16; ++n) asm volatile("" : "=r"(hh[n]), "=r"(mm[n]), "=r"(ll[n]));
+#else
             tmem_ld16(base, hh); tmem_ld16(base + kN, mm); tmem_ld16(base + 2 * kN, ll);          // columns 0-15
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#endif
             reg_fence16(hh); reg_fence16(mm); reg_fence16(ll);
+            if (q4 == 0) PROF_TL(s * kR + kg, 6);
+#if Y2_TC32_EXP != 1
 #pragma unroll
             for (int n = 0; n < 16; ++n) U[n % PPT] = tc32_step<SO>(U[n % PPT], hh[n], mm[n], ll[n]);     // (unrolled in column order = chain order per pixel)
+#else
+#pragma unroll
+            for (int n = 0; n < 16; ++n) U[n % PPT] ^= hh[n] ^ mm[n] ^ ll[n];
+#endif
+#if Y2_TC32_EXP == 2
+#pragma unroll
+            for (int n = 0; n < 16; ++n) asm volatile("" : "=r"(hh[n]), "=r"(mm[n]), "=r"(ll[n]));
+#else
             tmem_ld16(base + 16, hh); tmem_ld16(base + kN + 16, mm); tmem_ld16(base + 2 * kN + 16, ll);   // columns 16-31
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#endif
             reg_fence16(hh); reg_fence16(mm); reg_fence16(ll);
             // the whole tile has been read: hand the TMEM buffer to tile it+5
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(&go[slot + kBufs < kRing ? slot + kBufs : slot + kBufs - kRing]);
+            if (q4 == 0) PROF_TL(s * kR + kg, 7);
+#if Y2_TC32_EXP != 1
 #pragma unroll
             for (int n = 0; n < 16; ++n) U[(16 + n) % PPT] = tc32_step<SO>(U[(16 + n) % PPT], hh[n], mm[n], ll[n]);
+#else
+#pragma unroll
+            for (int n = 0; n < 16; ++n) U[(16 + n) % PPT] ^= hh[n] ^ mm[n] ^ ll[n];
+#endif
+            if (q4 == 0) PROF_TL(s * kR + kg, 8);
             slot += kR;
             if (slot >= kRing) { slot -= kRing; sph ^= 1; }
             tb = tb >= kBufs - kR ? tb - (kBufs - kR) : tb + kR;
@@ -590,6 +647,23 @@ int launch_conv_i16_tc32(const ConvFastParams &cp, int ksize, int ifm, int tn, c
     dim3 grid((unsigned)(((long long)cp.B * cp.H * cp.W + pt - 1) / pt), ceil_div(cp.OFM, kM));
     const bool ok = ksize == 3 ? dispatch_tn<3>(p, cp.so, tn, grid, smem, st) : dispatch_tn<1>(p, cp.so, tn, grid, smem, st);
     if (!ok) return -1;
+#ifdef Y2_TC32_PROFILE
+    if (cudaDeviceSynchronize() == cudaSuccess && (long long)p.nslices * kR >= Y2_TC32_TL0 + 48 && grid.x > 1) {
+        static long long tl[48 * 16];
+        cudaMemcpyFromSymbol(tl, g_tc32_tl, sizeof(tl));
+        fprintf(stderr, "tc32 timeline (CTA 1,0; tn %d, %d slices), cycles relative to the first event; per tile: slot free | built | w_full | go | issued | "
+                        "mma_done | half read | released | computed | loader: w_empty | issued\n", tn, p.nslices);
+        long long t0 = 0;
+        for (int i = 0; i < 48 * 16; ++i) if (tl[i] && (!t0 || tl[i] < t0)) t0 = tl[i];
+        for (int t = 0; t < 48; ++t) {
+            fprintf(stderr, "  tile %3d (slice %3d r %d):", Y2_TC32_TL0 + t, (Y2_TC32_TL0 + t) / kR, (Y2_TC32_TL0 + t) % kR);
+            for (int e = 0; e < 11; ++e) fprintf(stderr, " %6lld", tl[t * 16 + e] ? tl[t * 16 + e] - t0 : -1);
+            fprintf(stderr, "\n");
+        }
+        memset(tl, 0, sizeof(tl));
+        cudaMemcpyToSymbol(g_tc32_tl, tl, sizeof(tl));
+    }
+#endif
     if (variant)
         *variant = tn == 32 ? (ksize == 3 ? "conv_i16_tc32<3>" : "conv_i16_tc32<1>")
                  : tn == 16 ? (ksize == 3 ? "conv_i16_tc32<3,tn16>" : "conv_i16_tc32<1,tn16>")
