@@ -61,11 +61,19 @@ __device__ long long g_tc32_tl[48 * 16];
 #define PROF_TL(tile, ev)
 #endif
 constexpr int kEpiWarps = 12;       // warps 0-11: group kg = warp/4, TMEM lane quadrant = warp%4
-constexpr int kBuilder = 12;        // warps 12-14
-constexpr int kLoader = 15;         // warp 15: weight ring
-constexpr int kIssuer = 16;         // warps 16-18; warp 19 idles
-constexpr int kThreads = 20 * 32;
-constexpr int kEpiRegs = 120, kHelperRegs = 56;   // setmaxnreg (see conv_i16_tc2.cu): 8 x 32 x (96-56) = 10240 >= 12 x 32 x (120-96) = 9216
+constexpr int kBuilder = 12;        // warps 12-17: builder b builds tile b % 3 of the K slices with parity b / 3
+constexpr int kNB = 6;
+constexpr int kStager = 18;         // warp 18: activation staging (cp.async copy table walk), double-buffered chunks
+constexpr int kLoader = 19;         // warp 19: weight ring
+constexpr int kIssuer = 20;         // warps 20-22
+constexpr int kStager2 = 23;        // warp 23: second half of the staging copies
+constexpr int kThreads = 24 * 32;
+// setmaxnreg moves registers inside the CTA's own pool only (USETMAXREG.TRY_ALLOC.CTAPOOL): what the 12 helper warps hand back
+// (launch allocation 80 per thread at 768 threads) must cover what the 12 epilogue warps take: 80 - 48 >= 112 - 80.  (120 / 48 adds up
+// against the 64 K register file but not against the pool: the epilogue warps spin in TRY_ALLOC for ever - the hang of the first
+// six-builder build.)
+constexpr int kLaunchRegs = 80, kEpiRegs = 112, kHelperRegs = 48;
+static_assert(kEpiRegs - kLaunchRegs <= kLaunchRegs - kHelperRegs && kLaunchRegs * kThreads <= 65536, "setmaxnreg pool");
 constexpr int kWBytes = 2 * kM * 32;
 constexpr int kBBytes = kN * 32;    // one plane of one activation tile
 static_assert(kRing % kR == 0 && kRing % kBufs != 0, "slot -> fixed tile index");
@@ -208,7 +216,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
     unsigned long long *w_full = bars, *w_empty = w_full + kWRing, *go = w_empty + kWRing, *mma_done = go + kRing;
     // go[slot]: the tile in this ring slot may be issued = its activation tile is built (1 arrival, builder) AND its TMEM buffer
     // it % 5 has been read out by the epilogue of tile it-5 (4 arrivals; pre-arrived for the first five tiles)
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(mma_done + kRing + 1);
+    // x_full[b]: staging chunk buffer b holds its chunk (64 arrivals: the two staging warps' lanes, each after its own copies landed);
+    // x_empty[b]: every builder warp is past the slices that read it (6 arrivals)
+    unsigned long long *x_full = mma_done + kRing, *x_empty = x_full + 2;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(x_empty + 2 + 1);
     int *pxtab = reinterpret_cast<int *>(tmem_slot + 4);         // [96][4]: smem pixel offset for tap rows 0..2, valid flag
     int *rowinfo = pxtab + kPT * 4;                              // [32][2]: per staged row slot: first needed column, prefix of the copy table
     int2 *ctab = reinterpret_cast<int2 *>(rowinfo + 64);         // copy table of one C4 group plane: (global pixel offset, smem pixel offset)
@@ -226,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
     if (tid == 0) {
         for (int i = 0; i < kWRing; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], kR); }
         for (int i = 0; i < kRing; ++i) { mbar_init(&go[i], 5); mbar_init(&mma_done[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 64); mbar_init(&x_empty[i], kNB); }
         for (int i = 0; i < kBufs; ++i)
             for (int k = 0; k < 4; ++k) mbar_arrive(&go[i]);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -292,12 +304,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
     asm volatile("tcgen05.fence::after_thread_sync;");
     const unsigned tmem = *tmem_slot;
 
+    // ===== activation staging (warps kStager and kStager2, 64 lanes): chunk c = GS consecutive C4 group planes of the CTA's band, copied
+    // by walking the copy table (one cp.async per (group, needed pixel)).  The builders must never have copies of their own in flight:
+    // their per-tile fence (MEMBAR) would wait for them (measured: a 5.8 k-cycle builder stall per chunk with the copies on the
+    // builder warps, profiles/r2_tc32_timeline_3builders_tn32.txt) =====
+    auto stage_loop = [&](int li) {
+        const int nchunks = (p.G + GS - 1) >> p.gs_shift;
+        const int per_group = rowinfo[2 * (p.rows_max - 1) + 1];
+        const long long plane = (long long)p.H * p.W;
+        for (int c = 0; c < nchunks; ++c) {
+            if (c >= 2) mbar_wait(&x_empty[c & 1], ((c >> 1) - 1) & 1);
+            uint2 *dst = sX + (c & 1) * chunk_px;
+            const int g0 = c << p.gs_shift, ng = min(GS, p.G - g0);
+            int gg = 0, rem = li;                            // entry idx = gg * per_group + rem, idx = li, li + 64, ...
+            while (rem >= per_group) { rem -= per_group; ++gg; }
+            while (gg < ng) {
+                const int2 e = ctab[rem];
+                cp_async8(dst + gg * p.rows_max * p.PW + e.y, p.in + (g0 + gg) * plane + e.x);
+                rem += 64;
+                while (rem >= per_group) { rem -= per_group; ++gg; }
+            }
+            asm volatile("cp.async.commit_group;");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            mbar_arrive(&x_full[c & 1]);
+        }
+    };
+
     if (warp >= kEpiWarps) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHelperRegs));
         if (warp >= kIssuer) {
             // ===== three MMA issuer warps: warp iw issues tile iw of every step =====
             const int iw = warp - kIssuer;
-            if (iw < kR) {
+            if (warp == kStager2) {
+                stage_loop(32 + lane);
+            } else if (iw < kR) {
                 const unsigned long long dA0 = smem_desc(sW), dB0 = smem_desc(sB);
                 constexpr unsigned long long kAStep = kWBytes >> 4, kAPlane = (kM * 32) >> 4;      // descriptor address units (16 B)
                 constexpr unsigned long long kBStep = (2 * kBBytes) >> 4, kBPlane = kBBytes >> 4;
@@ -344,47 +384,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
                     PROF_TL(s * kR, 10);
                 }
             }
-        } else {
-            // ===== three builder warps: stage activations (cp.async); lane = one COLUMN of tile bw = (step slot sp, pixel): it gathers
-            // the TNW channels of its step's rounding group (TNW/4 C4 words) at its pixel + tap and writes the hi / lo byte planes of
-            // its B-operand row (row = column, K = 32 bytes: zero outside the K rows TNW*sp .. TNW*sp + TNW - 1) =====
-            const int bw = warp - kBuilder;
-            const int bi = bw * 32 + lane;              // builder thread index (staging)
+        } else if (warp == kStager) {
+            stage_loop(lane);
+        } else if (warp < kStager) {
+            // ===== six builder warps; lane = one COLUMN of tile bw = (step slot sp, pixel): it gathers the TNW channels of its step's
+            // rounding group (TNW/4 C4 words) at its pixel + tap and writes the hi / lo byte planes of its B-operand row (row = column,
+            // K = 32 bytes: zero outside the K rows TNW*sp .. TNW*sp + TNW - 1).  Two warps per tile index, alternating K slices: one
+            // warp's build of a slice is a ~1.3 k-cycle dependent chain (timeline of the three-builder form,
+            // profiles/r2_tc32_timeline_3builders_tn32.txt), which was the period of the whole pipeline =====
+            const int bidx = warp - kBuilder;
+            const int bw = bidx % kR, par = bidx / kR;
             const int sp = lane / PPT;                  // step slot of this lane's column within a K slice
             const int bt = bw * PPT + (lane % PPT);     // the CTA pixel this lane owns
-            constexpr int kBT = kR * 32;
-            const int nchunks = (p.G + GS - 1) >> p.gs_shift;
-            auto stage_chunk = [&](int c) {
-                uint2 *dst = sX + (c & 1) * chunk_px;
-                const int g0 = c << p.gs_shift, ng = min(GS, p.G - g0);
-                const int per_group = rowinfo[2 * (p.rows_max - 1) + 1];
-                const long long plane = (long long)p.H * p.W;
-                for (int idx = bi; idx < ng * per_group; idx += kBT) {
-                    const int gg = idx / per_group;
-                    const int2 e = ctab[idx - gg * per_group];
-                    cp_async8(dst + gg * p.rows_max * p.PW + e.y, p.in + (g0 + gg) * plane + e.x);
-                }
-                asm volatile("cp.async.commit_group;");
-            };
             const int r0 = operand_off(lane, 0), r1 = operand_off(lane, 16);   // this column's two 16-byte K chunks
             const int pxo0 = pxtab[bt * 4 + 0], pxo1 = pxtab[bt * 4 + 1], pxo2 = pxtab[bt * 4 + 2];
-            stage_chunk(0);
-            int staged = 0, ready = -1;
-            int slot = bw, sph = 0;
-            for (int sl = 0; sl < p.nslices; ++sl) {
+            int ready = -1, released = -1;              // highest chunk waited for / handed back
+            for (int sl = par; sl < p.nslices; sl += 2) {
+                const int slot = bw + kR * (sl & 3), sph = (sl >> 2) & 1;       // ring slot of tile (sl, bw) and its phase parity
                 // the chunks holding the C4 words of this slice's first and last step (warp-uniform; a slice spans at most two)
                 const int st_lo = sl * S, st_hi = min(st_lo + S, p.nsteps) - 1;
                 const int c_lo = ((st_lo / K2) * GW) >> p.gs_shift, c_hi = ((st_hi / K2) * GW) >> p.gs_shift;
-                if (staged + 1 < nchunks && staged <= c_lo) {
-                    bar_sync_named(1, kBT);             // every builder is past the slices that read chunk staged-1
-                    stage_chunk(staged + 1);
-                    ++staged;
+                while (released + 1 < c_lo) {           // this warp reads nothing below chunk c_lo any more
+                    ++released;
+                    if (lane == 0) mbar_arrive(&x_empty[released & 1]);
                 }
-                if (ready < c_hi) {
-                    if (staged > c_hi) asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    bar_sync_named(1, kBT);             // all builder warps see each other's copies
-                    ready = c_hi;
+                while (ready < c_hi) {
+                    ++ready;
+                    mbar_wait(&x_full[ready & 1], (ready >> 1) & 1);
                 }
                 if (sl >= kRing / kR) mbar_wait(&mma_done[slot], sph ^ 1);   // the MMAs of the previous tile in this slot have read it
                 PROF_TL(sl * kR + bw, 0);
@@ -430,8 +456,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_i16_tc32_kernel(const Tc32Pa
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&go[slot]);
                 PROF_TL(sl * kR + bw, 1);
-                slot += kR;
-                if (slot >= kRing) { slot -= kRing; sph ^= 1; }
+            }
+            // (a warp whose last slice ends below the last chunks still owes their hand-back: the staging warp waits for all six)
+            const int nchunks = (p.G + GS - 1) >> p.gs_shift;
+            while (released + 1 < nchunks - 2) {
+                ++released;
+                if (lane == 0) mbar_arrive(&x_empty[released & 1]);
             }
         }
     } else {
@@ -556,11 +586,21 @@ void launch_one(const Tc32Params &p, dim3 grid, size_t smem, cudaStream_t st)
     conv_i16_tc32_kernel<KS, SO, TNW><<<grid, kThreads, smem, st>>>(p);
 }
 
+// the setmaxnreg arithmetic above assumes the launch allocation ptxas chose; a build that allocates fewer registers per thread would
+// leave the epilogue warps waiting for registers for ever, so the launcher refuses instead
+template <int KS, int SO, int TNW>
+bool pool_ok()
+{
+    cudaFuncAttributes fa{};
+    if (cudaFuncGetAttributes(&fa, conv_i16_tc32_kernel<KS, SO, TNW>) != cudaSuccess) return false;
+    return kEpiRegs - fa.numRegs <= fa.numRegs - kHelperRegs;
+}
+
 template <int KS, int TNW>
 bool dispatch_so(const Tc32Params &p, int so, dim3 grid, size_t smem, cudaStream_t st)
 {
     switch (so) {
-#define Y2_TC32_CASE(S) case S: launch_one<KS, S, TNW>(p, grid, smem, st); return true;
+#define Y2_TC32_CASE(S) case S: if (!pool_ok<KS, S, TNW>()) return false; launch_one<KS, S, TNW>(p, grid, smem, st); return true;
         Y2_TC32_CASE(8) Y2_TC32_CASE(9) Y2_TC32_CASE(10) Y2_TC32_CASE(11) Y2_TC32_CASE(12) Y2_TC32_CASE(13) Y2_TC32_CASE(14)
         Y2_TC32_CASE(15) Y2_TC32_CASE(16)
 #undef Y2_TC32_CASE
