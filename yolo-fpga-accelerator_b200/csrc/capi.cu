@@ -985,7 +985,10 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
             bool tcn = false;
             if (tcn_shape && (ctx->Tn == 16 || ctx->Tn == 8) && l.fast && ctx->use_tc != 0) {
                 const int slices = conv_i16_tc32_slices(l.d.c, l.d.size, ctx->Tn);
-                tcn = ctx->use_tc > 0 || (long long)slices * l.d.n >= (long long)(ctx->Tn == 16 ? 8 : 16) * ceil_div(l.d.n, 128) * 128;
+                const bool fill80 = l.d.n * 5 >= ceil_div(l.d.n, 128) * 128 * 4;      // 1x1 layers: the staging warps bound the kernel, a half-empty
+                                                                                      // tile loses (512->64 1x1 @26, Tn = 16: 0.119 against 0.097 ms)
+                tcn = ctx->use_tc > 0 || ((long long)slices * l.d.n >= (long long)(ctx->Tn == 16 ? 8 : 16) * ceil_div(l.d.n, 128) * 128 &&
+                                          (l.d.size == 3 || fill80));
             }
             if (tcn_shape && ((!l.fast && ctx->Tn == 32) || tcn)) {
                 // reference built with Tn = 32 / 16 / 8: tensor-core kernel, one MMA K slice per 1 / 2 / 4 rounding groups
