@@ -313,10 +313,10 @@ def main():
                 "exact_steps_per_s_all_conv": conv_steps * last_chunk / (conv_ms * 1e-3),
                 "note": ("the reference rounds+saturates every 4 MACs (Tn=4), so every one of the 3.695 G steps of a frame needs CUDA-core "
                          "work beside the tensor cores: 2 SASS instr per step on the no-saturation fast path (range-checked per K-block, "
-                         "exact 4-instr step otherwise), and the kernel is bound by the issue slots of the SM sub-partitions (75 % busy in "
-                         "ncu, profiles/r2_conv_i16_tc2_ncu_full_summary.csv) and the TMEM hand-off, not by the tensor pipe (35 % busy); "
-                         "DESIGN.md section 4.  A reference built with Tn=32 runs at ~2.9 k frames/s on the Tn=32 variant of the same "
-                         "kernel (profiles/r1_layer_table_int16_b256_tn32.json)") if not fp32 else
+                         "exact 4-instr step otherwise), and the kernel is bound by the issue slots of the SM sub-partitions (79 % busy in "
+                         "ncu, profiles/r2_conv_i16_tc2_final_ncu_full_summary.csv) and the TMEM hand-off, not by the tensor pipe (39 % busy); "
+                         "DESIGN.md section 4.  A reference built with Tn=32 runs at ~3.1 k frames/s on the Tn=32 variant of the same "
+                         "kernel (profiles/r2_layer_table_int16_b64_tn32_final.json)") if not fp32 else
                         "fp32 build of the reference (hls/core/core_compute.cpp:121-172): plain FFMA chains on the CUDA cores"}
     # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of the same command's launches,
     # captured once under ncu and committed (profiles/r2_tc2_traffic.json, written by profiles/ncu_traffic.py); null when absent
