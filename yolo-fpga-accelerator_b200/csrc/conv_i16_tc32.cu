@@ -15,13 +15,16 @@
 //   t = 256*M + LL + half;  d = HH * 2^(16-so) + (t >> so);  acc = max(min(acc + d, 65535), 0)      (8 <= so <= 16).
 //
 // Tile = 128 output channels x 32 pixels x one step (N = 32 columns per plane, 96 TMEM columns, five buffers).  A CTA owns 96
-// consecutive pixels = three tiles; tile r of every step belongs to epilogue group r (its 32 accumulators per thread stay in
-// registers for the whole layer), to builder warp r (which gathers the 32 channels of its 32 pixels from the staged C4 patch and
-// writes the hi/lo byte planes of the B operand) and to issuer warp r.  Weights are the A operand from shared memory (one 8 KB
-// canonical tile per step, streamed by cp.async.bulk through a 4-slot ring): with N = 32 the MMA is shared-memory bound at
-// 40 cycles (profiles/microbench/umma_issue.cu), 160 cycles per 4096-step tile, which the ~300-cycle TMEM hand-off loop
-//  hides.  The barrier ring has 12 = 4 steps x 3 tiles slots: slot -> fixed tile index r, so every barrier's
-// consecutive phases are awaited by the same warp.
+// consecutive pixels = three tiles; tile r of every K slice belongs to epilogue group r (its accumulators stay in registers for
+// the whole layer), to the builder warps r and r + 3 (even / odd slices: each lane gathers the channels of its column from the
+// staged C4 patch and writes the hi/lo byte planes of its B-operand row) and to issuer warp r.  Two staging warps walk the copy
+// table of the CTA's activation band (cp.async, chunks of 16 C4 planes, double buffered) - on warps of their own, because the
+// builders' proxy fence (MEMBAR.ALL.CTA) waits for the issuing warp's outstanding copies.  Weights are the A operand from shared
+// memory (one 8 KB canonical tile per K slice, streamed by cp.async.bulk through a 4-slot ring): with N = 32 the MMA is
+// shared-memory bound at 40 cycles (profiles/microbench/umma_issue.cu), 160 cycles per 4096-step tile.  The barrier ring has
+// 12 = 4 slices x 3 tiles slots: slot -> fixed tile index r.  What bounds it (per-tile timelines, profiles/r2_tc32_timeline_*.txt):
+// the three-builder form of round 1 was builder bound (~1400 cycles per K slice); this form waits for the weight ring
+// (~2.9 k cycles per 8 KB tile, four slices deep).  DESIGN.md section 4, "Rounding-group variants".
 #include "common.cuh"
 #ifdef Y2_TC32_PROFILE
 #include <cstdio>
