@@ -244,3 +244,27 @@ def test_pass_size_model_follows_the_persistent_kernel():
     assert tiles[0] is None                                        # 3 input channels: conv_i16_g1_kernel
     assert [i for i, t in tiles.items() if t == (64, 96)] == [2, 5, 26]      # 64 output channels: HALF mode
     assert all(t == (128, 48) for i, t in tiles.items() if i not in (0, 2, 5, 26))
+
+
+def test_variant_tensor_core_kernel_register_pool_balances():
+    """csrc/conv_i16_tc32.cu re-splits registers between its warp roles with setmaxnreg, which moves registers inside the CTA's OWN
+    pool only: what the helper warps hand back below the launch allocation must cover what the epilogue warps take above it, or
+    the epilogue spins in USETMAXREG.TRY_ALLOC for ever (the hang of the first six-builder build).  Checked here against the
+    launch allocation ptxas reports for every instantiation in the build log, and: no instantiation spills."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "yolo-fpga-accelerator_b200")
+    src = open(os.path.join(pkg, "csrc", "conv_i16_tc32.cu")).read()
+    log_path = os.path.join(pkg, "lib", "conv_i16_tc32.ptxas.log")
+    if not os.path.exists(log_path):
+        pytest.skip("library not built here (make writes lib/*.ptxas.log)")
+    log = open(log_path).read()
+    m = re.search(r"kLaunchRegs = (\d+), kEpiRegs = (\d+), kHelperRegs = (\d+)", src)
+    launch, epi, helper = (int(v) for v in m.groups())
+    threads = 32 * int(re.search(r"kThreads = (\d+) \* 32", src).group(1))
+    epi_warps = int(re.search(r"kEpiWarps = (\d+)", src).group(1))
+    helper_warps = threads // 32 - epi_warps
+    assert launch * threads <= 65536
+    assert epi_warps * (epi - launch) <= helper_warps * (launch - helper)
+    used = [int(v) for v in re.findall(r"Used (\d+) registers, used 1 barriers", log)]
+    assert len(used) == 54 and set(used) == {launch}, sorted(set(used))          # 2 kernel sizes x 9 shifts x 3 rounding groups
+    assert not re.search(r"[1-9]\d* bytes spill", log)

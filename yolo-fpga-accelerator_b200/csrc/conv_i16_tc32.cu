@@ -98,18 +98,6 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
         "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ unsigned mbar_test(void *bar, unsigned parity)   // non-blocking probe
-{
-    unsigned ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok;
-}
 __device__ __forceinline__ void mbar_arrive(void *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -145,12 +133,6 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, int *r)
                    "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_st8(unsigned taddr, const uint4 &a, const uint4 &b)
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(a.x), "r"(a.y), "r"(a.z),
-                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-                 : "memory");
-}
 // ties the registers of an asynchronous tcgen05.ld to the point after tcgen05.wait::ld
 __device__ __forceinline__ void reg_fence16(int *r)
 {
@@ -162,7 +144,6 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
 }
-__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // K-major, no-swizzle canonical operand: core matrix = 8 rows x 16 bytes, contiguous (128 B);
 // the two K chunks of a 32-byte row are LBO = 128 B apart, 8-row groups are SBO = 256 B apart.
