@@ -31,6 +31,7 @@ def ref_net_forward(ref, net, frame, pack, keep_layers=False, helper: Oracle = N
     YOLO2_FPGA + host ops, excluding setup)."""
     from yolo2_b200.accel import conv_call_args, pool_call_args  # argument recipe of yolo2_model.cpp:299-355
     helper = helper or Oracle()
+    tn, tm = getattr(ref, "tn", 4), getattr(ref, "tm", 32)        # the tile parameters this reference build was compiled with
     i16 = pack.is_int16
     dt = np.int16 if i16 else np.float32
     slack = 8192
@@ -49,7 +50,7 @@ def ref_net_forward(ref, net, frame, pack, keep_layers=False, helper: Oracle = N
     t0 = time.perf_counter()
     for i, l in enumerate(net.layers):
         if l.type == CONV:
-            a = conv_call_args(l.c, l.n, l.size, l.stride, l.w, l.h, l.pad, l.leaky, l.batch_normalize)
+            a = conv_call_args(l.c, l.n, l.size, l.stride, l.w, l.h, l.pad, l.leaky, l.batch_normalize, tn=tn, tm=tm)
             q = (0, 0, 0, 0)
             if i16:
                 qa_in = int(aq[ci]) if ci < len(aq) else current_qa
@@ -73,7 +74,7 @@ def ref_net_forward(ref, net, frame, pack, keep_layers=False, helper: Oracle = N
             boff += l.n
             ci += 1
         elif l.type == MAXPOOL:
-            a = pool_call_args(l.c, l.size, l.stride, l.w, l.h, l.out_w, l.out_h, l.pad)
+            a = pool_call_args(l.c, l.size, l.stride, l.w, l.h, l.out_w, l.out_h, l.pad, tn=tn, tm=tm)
             buf = np.zeros(cur.size + 2 * slack, dt)
             buf[slack:slack + cur.size] = cur.reshape(-1)
             out = np.zeros((l.out_c, l.out_h, align8(l.out_w)), dt)

@@ -147,3 +147,28 @@ def test_conv_int16_variant_builds(tn, oracle):
         want = ref.run_layer(x, wr, b, a, q)
         got = oracle_conv(oracle, a, x, wr, b, q)
         assert np.array_equal(valid(got, w), valid(want, w))
+
+
+@pytest.mark.parametrize("tn,table", [(8, "default"), (16, "stress"), (32, "default")])
+def test_net_forward_variant_builds(tn, table, oracle):
+    """a whole (thin) YOLOv2 through the unmodified YOLO2_FPGA of a reference COMPILED with Tn = tn, layer by layer
+    (oracle/ref_driver.py), against the oracle's net forward with the same tile parameters: every ofm and the region tensor bit for
+    bit.  This pins the checker the GPU tests of the rounding-group variants use (test_whole_net_rounding_group_variant,
+    test_full_width_rounding_group_variant)."""
+    from oracle.oracle import Ref, have_ref
+    if not have_ref("int16", tn):
+        pytest.skip(f"oracle/_ref/libref_int16_tn{tn}.so not built (make -C oracle ref-variants)")
+    ref = Ref("int16", tn)
+    net = ycfg.parse_network_cfg(ycfg.yolov2_cfg_text(416, 416, 3, channel_div=8))
+    pack = yw.synth_pack(net, "int16", seed=31 + tn, table=table, tn=tn)
+    frame = yw.synth_frames(net, 1, seed=500 + tn)[0]
+    oracle.set_tile_params(tn, 32)
+    try:
+        want_region, want_dumps, _ = ref_net_forward(ref, net, frame, pack, keep_layers=True, helper=oracle)
+        got_region, got_dumps = oracle.net_forward(net, frame, pack, dump_layers=True)
+    finally:
+        oracle.set_tile_params(4, 32)
+    for i, w in want_dumps.items():
+        ow = net.layers[i].out_w
+        assert np.array_equal(valid(got_dumps[i], ow), valid(w, ow)), f"tn {tn} layer {i}"
+    assert np.array_equal(got_region.view(np.uint32), want_region.view(np.uint32))

@@ -128,10 +128,10 @@ def conv_call_args(c, n, size, stride, w, h, pad, leaky, bn=0, tn=Tn, tm=Tm):
                 mLoopsxTM=mLoops * TM, mLoops_a1xTM=(mLoops + 1) * TM, LayerType=0)
 
 
-def pool_call_args(c, size, stride, w, h, out_w, out_h, pad):
+def pool_call_args(c, size, stride, w, h, out_w, out_h, pad, tn=Tn, tm=Tm):
     TR = min((OnChipIB - size) // stride + 1, Tr, out_h)
     TC = min((OnChipIB - size) // stride + 1, Tc, out_w)
-    TM = min(Tm, Tn, c)
+    TM = min(tm, tn, c)
     mLoops = math.ceil(c / TM)
     return dict(IFM_num=c, OFM_num=c, Ksize=size, Kstride=stride, Input_w=w, Input_h=h, Output_w=out_w, Output_h=out_h,
                 Padding=pad, IsNL=0, IsBN=0, TM=TM, TN=0, TR=TR, TC=TC, OFM_num_bound=(mLoops + 2) * TM,
