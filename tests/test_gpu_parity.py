@@ -607,7 +607,8 @@ def test_whole_net_rounding_group_variant(tn, tc, oracle, monkeypatch):
 
 @pytest.mark.parametrize("i", range(5))
 def test_tn_variant_golden_gpu(i):
-    """the CUDA path (generic kernel for Tn = 8, tcgen05 kernel for Tn = 32) against outputs of the reference built with that Tn"""
+    """the CUDA path (grouped CUDA-core kernel for Tn = 8 / 16 in this single-frame entry, tcgen05 kernel for Tn = 32) against outputs of
+    the reference built with that Tn"""
     from oracle.gen_golden import ARG_KEYS
     from yolo2_b200.accel import Accelerator
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layer_cases_tn_variants.npz"))

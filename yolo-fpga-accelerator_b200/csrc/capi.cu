@@ -1009,7 +1009,7 @@ int yolo2cuda_net_load_weights(yolo2cuda_net *net, const void *weights, size_t n
                 ConvFastParams p{};
                 p.B = net->max_batch; p.H = l.d.h; p.W = l.d.w; p.G = ceil_div(l.d.c, 4); p.OFM = l.d.n;
                 // rounding group of 4 channels (reference default, or a layer with <= 4 input channels under any Tn): every int16 kernel;
-                // Tn = 8 / 16 builds: 2 / 4 C4 words per step in the CUDA-core kernel only (the tcgen05 kernels implement Tn = 4 and 32)
+                // Tn = 8 / 16 builds: 2 / 4 C4 words per step in the CUDA-core kernel (the layers the variant tensor-core kernel did not take above)
                 const bool group4 = e == 4 || TN == 4 || l.d.c <= 4;
                 p.group_words = group4 ? 1 : ctx->Tn / 4;
                 if (conv_fast_plan(p, l.d.size, e) == 0) l.fast = false;
