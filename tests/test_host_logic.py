@@ -268,3 +268,57 @@ def test_variant_tensor_core_kernel_register_pool_balances():
     used = [int(v) for v in re.findall(r"Used (\d+) registers, used 1 barriers", log)]
     assert len(used) == 54 and set(used) == {launch}, sorted(set(used))          # 2 kernel sizes x 9 shifts x 3 rounding groups
     assert not re.search(r"[1-9]\d* bytes spill", log)
+
+
+@pytest.mark.parametrize("tn", [8, 16, 32])
+@pytest.mark.parametrize("c,n,k,w,h,q,amp", [(37, 5, 3, 6, 5, (13, 9, 12, 7), 32767), (20, 3, 1, 7, 4, (14, 10, 10, 10), 600),
+                                             (64, 4, 3, 5, 5, (12, 10, 8, 9), 4000)])
+def test_variant_tensor_core_decomposition_mirror(tn, c, n, k, w, h, q, amp, oracle):
+    """numpy mirror of what csrc/conv_i16_tc32.cu asks of the tensor cores and of the CUDA cores behind them, against the oracle
+    with TN = tn: per K = 32 slice the weight tile A (K byte kk = channel kk % tn of the rounding group of chain step
+    slice * 32/tn + kk / tn), the block-diagonal activation tile B (column (step slot, pixel) non-zero only in that slot's K rows),
+    signed-hi / unsigned-lo byte planes, HH / M / LL as three int32 products, then per column in chain order
+    t = 256 M + LL + half, d = HH 2^(16-so) + (t >> so), acc = clamp(acc + d) on the offset accumulator, leaky / 10."""
+    from helpers import make_conv_case, oracle_conv, valid
+    a, x, wr, b, wd = make_conv_case(7 * tn + c + k, c, n, k, 1, w, h, 1, amp=amp, xamp=32767 if amp > 600 else 2000, tn=tn)
+    Qw, Qa_in, Qa_out, Qb = q
+    so, sb = Qa_in + Qw - Qa_out, Qb - Qa_out
+    assert 8 <= so <= 16
+    want = valid(oracle_conv(oracle, a, x, wr, b, q), w)
+    K2, pad, S = k * k, k // 2, 32 // tn
+    nsteps = -(-c // tn) * K2
+    nslices = -(-nsteps // S)
+    xp = np.zeros((c, h + 2 * pad, w + 2 * pad), np.int64)
+    xp[:, pad:pad + h, pad:pad + w] = x[:, :, :w]
+    npix = h * w
+    rs = lambda v, s: (v + (1 << (s - 1))) >> s if s > 0 else v << -s          # round-half-up arithmetic shift
+    U = np.empty((n, npix), np.int64)
+    rb = (1 << (38 - so)) + 2
+    U[:] = np.clip(rs(b.astype(np.int64), sb) + 32768, -rb, 65535 + rb)[:, None]
+    for sl in range(nslices):
+        A = np.zeros((n, 32), np.int64)                                     # weights of the slice: row = output channel
+        B = np.zeros((32, S, npix), np.int64)                               # activations: column = (step slot, pixel)
+        for kk in range(32):
+            sp, t = kk // tn, kk % tn
+            step = sl * S + sp
+            g, tap = step // K2, step % K2
+            ch = g * tn + t
+            if step >= nsteps or ch >= c:
+                continue
+            A[:, kk] = wd[:, ch, tap]
+            ti, tj = tap // k, tap % k
+            B[kk, sp, :] = xp[ch, ti:ti + h, tj:tj + w].reshape(-1)          # only in the K rows of its own step slot
+        Ah, Al = A >> 8, A & 255                                            # signed hi, unsigned lo
+        Bh, Bl = B >> 8, B & 255
+        HH = np.einsum("mk,ksp->msp", Ah, Bh)
+        M = np.einsum("mk,ksp->msp", Ah, Bl) + np.einsum("mk,ksp->msp", Al, Bh)
+        LL = np.einsum("mk,ksp->msp", Al, Bl)
+        assert np.abs(M).max() < 2 ** 31 and np.abs(HH).max() < 2 ** 31      # int32 accumulators of the MMA suffice
+        for sp in range(S):                                                  # chain order; slots past the last step add d = 0
+            t = 256 * M[:, sp] + LL[:, sp] + (1 << (so - 1))
+            assert np.abs(t).max() < 2 ** 31
+            d = HH[:, sp] * (1 << (16 - so)) + (t >> so)
+            U = np.clip(U + d, 0, 65535)
+    out = U - 32768
+    out = np.where(out < 0, -((-out) // 10), out)                            # leaky: C division truncates toward zero
+    assert np.array_equal(out.reshape(n, h, w).astype(np.int16), want)
