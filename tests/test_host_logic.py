@@ -322,3 +322,76 @@ def test_variant_tensor_core_decomposition_mirror(tn, c, n, k, w, h, q, amp, ora
     out = U - 32768
     out = np.where(out < 0, -((-out) // 10), out)                            # leaky: C division truncates toward zero
     assert np.array_equal(out.reshape(n, h, w).astype(np.int16), want)
+
+
+@pytest.mark.parametrize("c,n,k,w,h,q,amp,xamp,known_xmax", [
+    (40, 6, 3, 6, 5, (14, 10, 10, 10), 600, 2000, True),       # the bench's default table: every K-block on the fast path
+    (40, 6, 3, 6, 5, (14, 10, 10, 10), 600, 2000, False),      # producer unknown: xmax = 32768 assumed, fewer fast blocks, same bits
+    (37, 5, 3, 5, 4, (13, 9, 12, 7), 32767, 32767, True),      # full range: saturating chain, mostly the exact step
+    (64, 4, 1, 7, 3, (12, 10, 6, 9), 3000, 9000, True),        # so = 16, 1x1
+    (21, 3, 3, 4, 4, (9, 8, 8, 8), 300, 500, True),            # so = 9
+    (48, 12, 3, 6, 6, (14, 10, 10, 6), 2500, 2000, True)])     # biases shifted left by 4: accumulators near both rails, fast and exact blocks mix
+def test_headline_kernel_fast_path_is_exact_mirror(c, n, k, w, h, q, amp, xamp, known_xmax, oracle):
+    """numpy mirror of the no-saturation fast path of csrc/conv_i16_tc2.cu (the reference's default Tn = 4): per K-block of seven chain
+    steps the kernel tests Dsum <= acc + 32768 <= 65535 - Dsum with Dsum = ((sum of the block's 28 |w|) * xmax >> so) + 8 and, when
+    it holds, replaces seven round-and-saturate steps by acc += 2^(16-so) * sum HH_s + sum ((256 M_s + LL_s + half) >> so).  Here
+    both forms run side by side on every (channel, pixel, K-block): wherever the test holds they must agree, the mixed result must be
+    the oracle's bits, and the test must not be vacuous (blocks pass in the moderate cases, the full-range case runs on the exact step)."""
+    from helpers import make_conv_case, oracle_conv, valid
+    a, x, wr, b, wd = make_conv_case(c * 31 + n + k, c, n, k, 1, w, h, 1, amp=amp, xamp=xamp)
+    Qw, Qa_in, Qa_out, Qb = q
+    so, sb = Qa_in + Qw - Qa_out, Qb - Qa_out
+    assert 8 <= so <= 16
+    want = valid(oracle_conv(oracle, a, x, wr, b, q), w)
+    K2, pad, G = k * k, k // 2, -(-c // 4)
+    nsteps = G * K2
+    nkb = -(-nsteps // 7)
+    xp = np.zeros((4 * G, h + 2 * pad, w + 2 * pad), np.int64)
+    xp[:c, pad:pad + h, pad:pad + w] = x[:, :, :w]
+    wz = np.zeros((n, 4 * G, K2), np.int64)
+    wz[:, :c] = wd
+    xmax = int(np.abs(x[:, :, :w].astype(np.int64)).max()) if known_xmax else 32768
+    npix = h * w
+    rs = lambda v, s: (v + (1 << (s - 1))) >> s if s > 0 else v << -s
+    rb = (1 << (33 - so)) + 2
+    U = np.empty((n, npix), np.int64)
+    U[:] = np.clip(rs(b.astype(np.int64), sb) + 32768, -rb, 65535 + rb)[:, None]
+    n_fast = n_exact = 0
+    for kb in range(nkb):
+        HH, T, wsum = [], [], np.zeros(n, np.int64)
+        for s in range(7):
+            sigma = kb * 7 + s
+            hh = np.zeros((n, npix), np.int64)
+            t = np.full((n, npix), 1 << (so - 1), np.int64)                   # the rounding constant rides in K row 28 of every step slot
+            if sigma < nsteps:
+                g, tap = sigma // K2, sigma % K2
+                ti, tj = tap // k, tap % k
+                W4 = wz[:, 4 * g:4 * g + 4, tap]                             # [n][4]
+                X4 = xp[4 * g:4 * g + 4, ti:ti + h, tj:tj + w].reshape(4, -1)  # [4][pix]
+                wh, wl, xh, xl = W4 >> 8, W4 & 255, X4 >> 8, X4 & 255
+                hh = wh @ xh
+                t = t + 256 * (wh @ xl + wl @ xh) + wl @ xl
+                assert np.array_equal(65536 * hh + t - (1 << (so - 1)), W4 @ X4)   # the four byte-plane products recombine to P
+                wsum += np.abs(W4).sum(axis=1)
+            HH.append(hh); T.append(t)
+        dsum = ((wsum * xmax) >> so) + 8
+        dsum = np.where(dsum > 40000, 1 << 30, dsum)[:, None]
+        ok = (U >= dsum) & (U <= 65535 - dsum)
+        exact = U.copy()
+        for s in range(7):
+            exact = np.clip(exact + HH[s] * (1 << (16 - so)) + (T[s] >> so), 0, 65535)
+        fast = U + (1 << (16 - so)) * sum(HH) + sum(ts >> so for ts in T)
+        assert np.array_equal(fast[ok], exact[ok]), f"K-block {kb}: the bound let a saturating block through"
+        n_fast += int(ok.sum()); n_exact += int((~ok).sum())
+        U = np.where(ok, fast, exact)
+    out = U - 32768
+    out = np.where(out < 0, -((-out) // 10), out)
+    assert np.array_equal(out.reshape(n, h, w).astype(np.int16), want)
+    if amp == 2500:
+        assert n_fast > 100 and n_exact > 100, (n_fast, n_exact)
+    if amp == 32767:
+        assert n_exact > n_fast          # (full-range operands: the bound exceeds the accumulator range, every block takes the exact step)
+    else:
+        assert n_fast > 0
+    if amp == 600 and known_xmax:
+        assert n_exact == 0
